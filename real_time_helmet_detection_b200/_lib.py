@@ -1,0 +1,80 @@
+"""ctypes binding of libhd_b200.so — the C-ABI boundary declared in include/hd_b200.h.
+
+There is no CPU fallback: if the shared library is missing or a kernel call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_void_p, c_float, c_size_t, c_char_p, c_longlong
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libhd_b200.so")
+
+_lib = None
+
+P = c_void_p
+I = c_int
+F = c_float
+
+# name -> (restype, argtypes)
+_SIGNATURES = {
+    "hd_last_error": (c_char_p, []),
+    "hd_version": (I, []),
+    "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "hd_conv2d_wgrad_ksplit": (I, [I, I, I, I]),
+    "hd_conv2d_wgrad_workspace_bytes": (c_size_t, [I, I, I, I, I]),
+    "hd_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, P]),
+    "hd_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, I, P]),
+    "hd_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, I, P]),
+}
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def register(name: str, restype, argtypes) -> None:
+    _SIGNATURES[name] = (restype, argtypes)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "There is no CPU fallback for this path.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(_lib, name)  # AttributeError if the .so is stale
+            fn.restype, fn.argtypes = restype, argtypes
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().hd_last_error()
+        raise RuntimeError(f"libhd_b200 {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> c_void_p | None:
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: this path has no CPU implementation")

@@ -1,0 +1,368 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), used for the forward pass and for
+// dgrad (same kernel, tap-flipped / transposed packed weights) of every 3x3 and 1x1 convolution
+// of the hourglass (reference: hourglass.py:94-108 `Convolution`, called from `Residual` :111-127,
+// `Neck` :176-186, `Head` :189-195 and the merge convs :215-218).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wp[tap, cout, cin]
+//
+// * Activations are NHWC bf16. One CTA tile = 128 output pixels (TN images x TH rows x TW columns,
+//   all powers of two) x BLOCK_N output channels.
+// * A operand: for every (tap, 64-channel chunk) one 4-D TMA box {64ch, TW, TH, TN} at the tap-shifted
+//   pixel coordinate; out-of-image coordinates are zero-filled by TMA, which is exactly the conv's
+//   zero padding. The box lands in smem as 128 rows of 128 B = the canonical K-major SWIZZLE_128B
+//   UMMA layout, so no im2col buffer ever exists.
+// * B operand: packed weights [tap][BLOCK_N][Cin] bf16, one 3-D TMA box {64, BLOCK_N, 1} per k-step.
+// * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16, fp32 accumulators in TMEM,
+//   double-buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+//   warps 4-7 = epilogue (TMEM -> registers -> bias / residual add / BN statistics -> global).
+// * Persistent: grid = min(tiles, #SM); tiles are taken round-robin.
+#include <cuda_bf16.h>
+
+#include "hd_common.h"
+#include "hd_ptx.cuh"
+
+namespace hd {
+
+constexpr int kStages = 6;
+constexpr int kABytes = 128 * 128;  // 128 pixel rows x 64 bf16
+constexpr int kThreads = 256;
+
+struct ConvParams {
+    int N, H, W;          // output == input spatial size (stride 1, "same" padding)
+    int cin_chunks;       // Cin / 64
+    int kh, kw, pad;      // taps
+    int cout;             // real output channels (<= BLOCK_N)
+    int tw_log2, th_log2, tn_log2;
+    int tiles_x, tiles_y, tiles_n, num_tiles;
+    // outputs
+    int out_mode;         // 0: NHWC bf16 (channel stride out_cs) ; 1: NCHW fp32 slice of (B,S,cout,H,W)
+    int out_cs;           // channel stride (elements) of the NHWC output
+    int stack_idx, num_stack;
+    void* out;
+    __nv_bfloat16* out2;  // optional second NHWC bf16 copy (channel stride out2_cs, zero padded), mode 1 only
+    int out2_cs;
+    const float* bias;        // optional [cout]
+    const __nv_bfloat16* addend;  // optional NHWC bf16, same shape as out (mode 0)
+    float* stat_sum;          // optional [cout] : sum over pixels of the fp32 conv output (bias included)
+    float* stat_sqsum;        // optional [cout]
+};
+
+// Sum v[0..31] across the 32 lanes of the warp; on return lane l holds the total of element l.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float send = upper ? v[i] : v[i + off];
+            float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const ConvParams p) {
+    constexpr int kBBytes = BLOCK_N * 128;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tmem_full = bars + 2 * kStages;
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BLOCK_N]
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    if (threadIdx.x < 2 * BLOCK_N) s_stat[threadIdx.x] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksteps = p.kh * p.kw * p.cin_chunks;
+    const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int tn = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << p.tn_log2;
+                for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+                    const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                    for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * kStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                        tma_load_4d(sa, &tmap_x, &full_bar[stage], ck * 64, x0 + dx, y0 + dy, n0);
+                        tma_load_3d(sa + kABytes, &tmap_w, &full_bar[stage], ck * 64, 0, tap);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        uint32_t stage = 0, phase = 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t adesc = umma_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t bdesc = umma_smem_desc_sw128(sa + kABytes, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in (addr>>4) units
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (ks > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (ks == ksteps - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue
+        const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = ew * 32 + (int)lane;     // tile row == TMEM lane
+        const bool do_stats = p.stat_sum != nullptr;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int tn = tile / (p.tiles_x * p.tiles_y);
+            const int x = (tx << p.tw_log2) + (row & (TW - 1));
+            const int y = (ty << p.th_log2) + ((row >> p.tw_log2) & (TH - 1));
+            const int n = (tn << p.tn_log2) + (row >> (p.tw_log2 + p.th_log2));
+            const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+            const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
+
+            if constexpr (BLOCK_N >= 32) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
+                    }
+                    if (p.addend && valid) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.out_cs + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u = __ldg(ap + q);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = __bfloat1622float2(h[j]);
+                                v[q * 8 + 2 * j] += f.x;
+                                v[q * 8 + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                             pix * p.out_cs + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                            op[q] = u;
+                        }
+                    }
+                    if (do_stats) {
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = valid ? v[i] : 0.f;
+                            sq[i] = v[i] * v[i];
+                        }
+                        float s1 = warp_transpose_reduce(v, lane);
+                        float s2 = warp_transpose_reduce(sq, lane);
+                        atomicAdd(&s_stat[c0 + lane], s1);
+                        atomicAdd(&s_stat[BLOCK_N + c0 + lane], s2);
+                    }
+                }
+            } else {
+                // BLOCK_N == 16: prediction head (hourglass.py:189-195), fp32 NCHW logits
+                uint32_t r[16];
+                tmem_ld_x16(taddr, r);
+                tmem_ld_wait();
+                if (valid) {
+                    const size_t hw = static_cast<size_t>(p.H) * p.W;
+                    float* o = reinterpret_cast<float*>(p.out) +
+                               (static_cast<size_t>(n) * p.num_stack + p.stack_idx) * p.cout * hw +
+                               static_cast<size_t>(y) * p.W + x;
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        if (p.bias && i < p.cout) v[i] += __ldg(p.bias + i);
+                        if (i >= p.cout) v[i] = 0.f;
+                    }
+                    if (p.out_mode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < p.cout) o[i * hw] = v[i];
+                    } else {
+                        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < p.cout) ob[i] = __float2bfloat16(v[i]);
+                    }
+                    if (p.out2) {
+                        uint4* o2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_cs);
+                        uint4 u0, u1;
+                        u0.x = pack_bf16x2(v[0], v[1]);   u0.y = pack_bf16x2(v[2], v[3]);
+                        u0.z = pack_bf16x2(v[4], v[5]);   u0.w = pack_bf16x2(v[6], v[7]);
+                        u1.x = pack_bf16x2(v[8], v[9]);   u1.y = pack_bf16x2(v[10], v[11]);
+                        u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+                        o2[0] = u0;
+                        o2[1] = u1;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+        if (do_stats) {
+            named_bar_sync(1, 128);
+            const int t = threadIdx.x - 128;
+            for (int c = t; c < BLOCK_N; c += 128) {
+                if (c < p.cout) {
+                    atomicAdd(p.stat_sum + c, s_stat[c]);
+                    atomicAdd(p.stat_sqsum + c, s_stat[BLOCK_N + c]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    constexpr int smem_bytes = kStages * (kABytes + BLOCK_N * 128) + 1024 /*align*/ + 256 /*barriers*/ +
+                               2 * BLOCK_N * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        attr_set = true;
+    }
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    conv_igemm_kernel<BLOCK_N><<<grid, kThreads, smem_bytes, stream>>>(tx, tw, p);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+}  // namespace hd
+
+// See include/hd_b200.h for the contract.
+extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                               const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
+                               int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx,
+                               int num_stack, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(cin % 64 == 0 && cin >= 64 && cin <= 512, "conv_igemm: cin=%d must be a multiple of 64", cin);
+    HD_REQUIRE(block_n == 128 || block_n == 64 || block_n == 16, "conv_igemm: block_n=%d unsupported", block_n);
+    HD_REQUIRE(cout >= 1 && cout <= block_n, "conv_igemm: cout=%d > block_n=%d", cout, block_n);
+    HD_REQUIRE(ksize == 1 || ksize == 3, "conv_igemm: ksize=%d unsupported", ksize);
+    HD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_igemm: empty tensor");
+    HD_REQUIRE(block_n != 16 || (addend == nullptr && stat_sum == nullptr), "conv_igemm: head variant has no addend/stats");
+    HD_REQUIRE(block_n == 16 || (out_mode == 0 && cout % 32 == 0 && out_cs % 8 == 0),
+               "conv_igemm: NHWC output needs cout %% 32 == 0");
+    HD_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "conv_igemm: stat pointers must come in pairs");
+
+    ConvParams p{};
+    p.N = N; p.H = H; p.W = W;
+    p.cin_chunks = cin / 64;
+    p.kh = p.kw = ksize;
+    p.pad = (ksize - 1) / 2;
+    p.cout = cout;
+    int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
+    int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
+    int tn = 128 / (tw * th);
+    p.tw_log2 = ilog2_ceil(tw); p.th_log2 = ilog2_ceil(th); p.tn_log2 = ilog2_ceil(tn);
+    p.tiles_x = (W + tw - 1) / tw; p.tiles_y = (H + th - 1) / th; p.tiles_n = (N + tn - 1) / tn;
+    p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    p.out_mode = out_mode; p.out_cs = out_cs; p.stack_idx = stack_idx; p.num_stack = num_stack;
+    p.out = out; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_cs = out2_cs;
+    p.bias = bias; p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
+    p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
+
+    alignas(64) CUtensorMap tmx, tmw;
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+        int rc = make_tmap_bf16(&tmx, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)block_n, (uint64_t)(ksize * ksize)};
+        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)block_n * cin * 2};
+        uint32_t box[3] = {64, (uint32_t)block_n, 1};
+        int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    if (block_n == 128) return launch_conv<128>(tmx, tmw, p, stream);
+    if (block_n == 64) return launch_conv<64>(tmx, tmw, p, stream);
+    return launch_conv<16>(tmx, tmw, p, stream);
+}

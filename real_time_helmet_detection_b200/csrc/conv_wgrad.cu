@@ -1,0 +1,270 @@
+// Weight-gradient of the 3x3 / 1x1 convolutions on tcgen05 tensor cores (sm_100a).
+// Autograd counterpart of nn.Conv2d inside hourglass.py:100 (`Convolution.convolution`), i.e.
+//
+//   dW[cout, cin, tap] = sum_{pixel} dY[pixel, cout] * X[pixel + tap, cin]
+//
+// GEMM view: M = cout (128), N = cin (64 | 128), K = pixels (B*H*W, split across CTAs).
+// Both operands are "MN-major" for UMMA: NHWC keeps the channel (M resp. N) contiguous and the
+// reduction dimension (pixels) strided, so the same 4-D TMA boxes as the forward kernel are used and
+// only the smem descriptors / instruction descriptor change (a_major = b_major = MN).
+//
+// Work split: grid = tap_groups x ksplit. A CTA owns one tap group (the three dx taps of one dy row for a
+// 3x3 kernel, or the single tap of a 1x1) and every ksplit-th 128-pixel tile; it keeps the group's
+// accumulators (3 x N fp32 columns) resident in TMEM over its whole pixel range, then writes one fp32
+// partial [tap][cout][cin] to the workspace. `hd_wgrad_reduce` sums the partials into the OIHW gradient.
+#include <cuda_bf16.h>
+
+#include "hd_common.h"
+#include "hd_ptx.cuh"
+
+namespace hd {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgBStages = 4;
+constexpr int kWgABytes = 2 * 128 * 128;  // dY tile: 128 pixels x 128 cout (two 64-channel atoms)
+
+struct WgradParams {
+    int N, H, W;
+    int kw, pad;               // taps per row, padding
+    int taps_per_group;        // 3 (3x3) or 1 (1x1)
+    int groups;                // 3 or 1
+    int ksplit;
+    int tw_log2, th_log2, tn_log2;
+    int tiles_x, tiles_y, num_tiles;
+    float* ws;                 // [ksplit][taps][128][BLOCK_N]
+    int taps;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradParams p) {
+    constexpr int kBBytes = 128 * BLOCK_N * 2;
+    constexpr int kNChunks = BLOCK_N / 64;
+    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 1, 1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                       // 2 buffers
+    uint8_t* smem_b = smem + 2 * kWgABytes;       // kWgBStages buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kBBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgBStages;
+    uint64_t* a_full = bars + 2 * kWgBStages;
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* tmem_full = a_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int group = blockIdx.x % p.groups;
+    const int split = blockIdx.x / p.groups;
+    const uint32_t tmem_cols_needed = p.taps_per_group * BLOCK_N;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_dy);
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < kWgBStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int tile = split; tile < p.num_tiles; tile += p.ksplit, ++it) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int tn = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << p.tn_log2;
+                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&a_empty[ab], aphase ^ 1);
+                mbar_arrive_expect_tx(&a_full[ab], kWgABytes);
+                tma_load_4d(smem_a + ab * kWgABytes, &tmap_dy, &a_full[ab], 0, x0, y0, n0);
+                tma_load_4d(smem_a + ab * kWgABytes + 128 * 128, &tmap_dy, &a_full[ab], 64, x0, y0, n0);
+                for (int t = 0; t < p.taps_per_group; ++t) {
+                    const int tap = group * p.taps_per_group + t;
+                    const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
+#pragma unroll
+                    for (int c = 0; c < kNChunks; ++c)
+                        tma_load_4d(smem_b + stage * kBBytes + c * 128 * 128, &tmap_x, &full_bar[stage], c * 64,
+                                    x0 + dx, y0 + dy, n0);
+                    if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (int tile = split; tile < p.num_tiles; tile += p.ksplit, ++it) {
+            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(&a_full[ab], aphase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem_a + ab * kWgABytes);
+            for (int t = 0; t < p.taps_per_group; ++t) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sb = smem_u32(smem_b + stage * kBBytes);
+                    // MN-major, 128B swizzle: LBO = stride between 64-channel atoms, SBO = stride between
+                    // 8-pixel groups along K.
+                    const uint64_t adesc = umma_smem_desc_sw128(sa, 128 * 128, 1024);
+                    const uint64_t bdesc = umma_smem_desc_sw128(sb, 128 * 128, 1024);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        // 16 pixels along K = 16 rows x 128 B = 2048 B -> +128 in (addr >> 4) units
+                        umma_bf16(tmem_base + t * BLOCK_N, adesc + 128 * k, bdesc + 128 * k, kIdesc,
+                                  (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&a_empty[ab]);
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        const int row = ew * 32 + (int)lane;  // cout
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        for (int t = 0; t < p.taps_per_group; ++t) {
+            const int tap = group * p.taps_per_group + t;
+            float* dst = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * 128 + row) * BLOCK_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + t * BLOCK_N + c0, r);
+                tmem_ld_wait();
+                float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    d4[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// grad[co][ci][tap] (+)= sum_s ws[s][tap][co][ci_pad]   (OIHW fp32, the layout of nn.Conv2d.weight.grad)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int ksplit, int taps,
+                                    int cout, int cin, int rows_pad, int cin_pad, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * cout * cin, ci fastest
+    const int total = taps * cout * cin;
+    if (idx >= total) return;
+    const int ci = idx % cin;
+    const int co = (idx / cin) % cout;
+    const int tap = idx / (cin * cout);
+    float s = 0.f;
+    const size_t stride = static_cast<size_t>(taps) * rows_pad * cin_pad;
+    const float* src = ws + (static_cast<size_t>(tap) * rows_pad + co) * cin_pad + ci;
+    for (int k = 0; k < ksplit; ++k) s += src[k * stride];
+    float* g = grad + (static_cast<size_t>(co) * cin + ci) * taps + tap;
+    *g = accumulate ? (*g + s) : s;
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
+    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * 128 * BLOCK_N * 2 + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        attr_set = true;
+    }
+    conv_wgrad_kernel<BLOCK_N><<<p.groups * p.ksplit, kWgThreads, smem_bytes, stream>>>(tdy, tx, p);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+}  // namespace hd
+
+extern "C" int hd_conv2d_wgrad_ksplit(int N, int H, int W, int ksize) {
+    using namespace hd;
+    int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
+    int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
+    int tn = 128 / (tw * th);
+    int tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th) * ((N + tn - 1) / tn);
+    int groups = ksize == 3 ? 3 : 1;
+    int ks = sm_count() / groups;
+    if (ks < 1) ks = 1;
+    if (ks > tiles) ks = tiles;
+    return ks;
+}
+
+extern "C" size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int ksize) {
+    int ks = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
+    return static_cast<size_t>(ks) * ksize * ksize * 128 * cin * sizeof(float);
+}
+
+// See include/hd_b200.h.
+extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W,
+                               int cin, int cin_real, int cout, int ksize, int accumulate, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(cout == 128, "conv_wgrad: cout=%d (tensor-core path needs 128)", cout);
+    HD_REQUIRE(cin == 64 || cin == 128, "conv_wgrad: cin=%d unsupported", cin);
+    HD_REQUIRE(cin_real >= 1 && cin_real <= cin, "conv_wgrad: cin_real=%d", cin_real);
+    HD_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize=%d unsupported", ksize);
+    HD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_wgrad: empty tensor");
+    WgradParams p{};
+    p.N = N; p.H = H; p.W = W;
+    p.kw = ksize; p.pad = (ksize - 1) / 2;
+    p.taps = ksize * ksize;
+    p.groups = ksize == 3 ? 3 : 1;
+    p.taps_per_group = ksize == 3 ? 3 : 1;
+    int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
+    int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
+    int tn = 128 / (tw * th);
+    p.tw_log2 = ilog2_ceil(tw); p.th_log2 = ilog2_ceil(th); p.tn_log2 = ilog2_ceil(tn);
+    p.tiles_x = (W + tw - 1) / tw; p.tiles_y = (H + th - 1) / th;
+    p.num_tiles = p.tiles_x * p.tiles_y * ((N + tn - 1) / tn);
+    p.ksplit = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
+    p.ws = reinterpret_cast<float*>(workspace);
+
+    alignas(64) CUtensorMap tdy, tx;
+    {
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
+        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+        int rc = make_tmap_bf16(&tdy, dy, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+        int rc = make_tmap_bf16(&tx, x, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    int rc = (cin == 128) ? launch_wgrad<128>(tdy, tx, p, stream) : launch_wgrad<64>(tdy, tx, p, stream);
+    if (rc) return rc;
+    const int total = p.taps * cout * cin_real;
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128,
+                                                                 cin, accumulate);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -1,0 +1,94 @@
+// Layout conversion kernels: OIHW fp32 master weights -> packed bf16 UMMA operand layouts, and
+// NCHW fp32 <-> NHWC bf16 activations (boundary of the nn.Module call signature, hourglass.py:223).
+#include <cuda_bf16.h>
+
+#include "hd_common.h"
+
+namespace hd {
+
+// mode 0 (forward): out[tap][r = co][k = ci] = w[co][ci][tap]
+// mode 1 (dgrad)  : out[tap][r = ci][k = co] = w[co][ci][taps-1-tap]   (180-degree rotated taps, transposed)
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
+                                   int taps, int rows_pad, int k_pad, int mode) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = taps * rows_pad * k_pad;
+    if (idx >= total) return;
+    const int k = idx % k_pad;
+    const int r = (idx / k_pad) % rows_pad;
+    const int tap = idx / (k_pad * rows_pad);
+    float v = 0.f;
+    if (mode == 0) {
+        if (r < cout && k < cin) v = w[(static_cast<size_t>(r) * cin + k) * taps + tap];
+    } else {
+        if (r < cin && k < cout) v = w[(static_cast<size_t>(k) * cin + r) * taps + (taps - 1 - tap)];
+    }
+    out[idx] = __float2bfloat16(v);
+}
+
+// x: [N, C, H, W] fp32 -> y: [N, H, W, c_pad] bf16 (channels >= C zero-filled)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H,
+                                    int W, int c_pad) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * H * W * c_pad;
+    if (idx >= total) return;
+    const int c = idx % c_pad;
+    const size_t pix = idx / c_pad;
+    const int wv = pix % W;
+    const int h = (pix / W) % H;
+    const int n = pix / (static_cast<size_t>(W) * H);
+    float v = 0.f;
+    if (c < C) v = x[((static_cast<size_t>(n) * C + c) * H + h) * W + wv];
+    y[idx] = __float2bfloat16(v);
+}
+
+// x: [N, H, W, c_stride] bf16 -> y: [N, C, H, W] fp32
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int H,
+                                    int W, int c_stride) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * C * H * W;
+    if (idx >= total) return;
+    const int wv = idx % W;
+    const int h = (idx / W) % H;
+    const int c = (idx / (static_cast<size_t>(W) * H)) % C;
+    const int n = idx / (static_cast<size_t>(W) * H * C);
+    y[idx] = __bfloat162float(x[((static_cast<size_t>(n) * H + h) * W + wv) * c_stride + c]);
+}
+
+}  // namespace hd
+
+extern "C" int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int ksize, int rows_pad,
+                                   int k_pad, int mode, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(mode == 0 || mode == 1, "pack_conv_weight: mode=%d", mode);
+    const int rows = mode == 0 ? cout : cin, kdim = mode == 0 ? cin : cout;
+    HD_REQUIRE(rows_pad >= rows && k_pad >= kdim, "pack_conv_weight: padding smaller than the matrix");
+    const int total = ksize * ksize * rows_pad * k_pad;
+    pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(out), cout,
+                                                                cin, ksize * ksize, rows_pad, k_pad, mode);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int c_pad,
+                                        cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(c_pad >= C, "nchw_to_nhwc: c_pad < C");
+    const size_t total = static_cast<size_t>(N) * H * W * c_pad;
+    if (total == 0) return HD_OK;
+    nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), N,
+                                                                            C, H, W, c_pad);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, int c_stride,
+                                        cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(c_stride >= C, "nhwc_to_nchw: c_stride < C");
+    const size_t total = static_cast<size_t>(N) * C * H * W;
+    if (total == 0) return HD_OK;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                            y, N, C, H, W, c_stride);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}

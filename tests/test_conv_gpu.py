@@ -1,0 +1,121 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution kernels (forward / dgrad / wgrad) against a plain
+PyTorch fp32 convolution on the same bf16-rounded operands (reference op: hourglass.py:100 nn.Conv2d).
+
+Tolerance: inputs are exactly representable in bf16 on both sides, products accumulate in fp32 on both sides,
+so the only differences are summation order and the final bf16 rounding of the NHWC output
+(2^-9 relative): |err| <= 1e-2 * max|ref| elementwise and relative L2 error <= 3e-3.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+CASES = [
+    # N, H, W, cin, cout, k
+    (2, 32, 32, 128, 128, 3),
+    (2, 16, 16, 128, 128, 3),
+    (3, 8, 8, 128, 128, 3),
+    (2, 4, 4, 128, 128, 3),
+    (5, 2, 2, 128, 128, 3),
+    (1, 64, 64, 64, 128, 3),
+    (1, 64, 64, 64, 128, 1),
+    (2, 32, 32, 128, 128, 1),
+    (1, 40, 24, 128, 128, 3),   # tiles that do not divide the image (masked rows)
+    (2, 5, 5, 128, 128, 3),
+    (1, 128, 128, 128, 128, 3),
+]
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k", CASES)
+def test_conv_forward(cuda_device, N, H, W, cin, cout, k):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(1234 + H * 7 + cin)
+    x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
+    w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    bias = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, bias, padding=(k - 1) // 2)
+
+    xd = ops.to_nhwc(x.to(cuda_device))
+    wp = ops.pack_weight(w.to(cuda_device), mode=0)
+    stats = torch.zeros(2, cout, device=cuda_device)
+    y = ops.conv2d_igemm(xd, wp, cout, k, bias=bias.to(cuda_device), stats=stats)
+    out = ops.to_nchw(y).cpu()
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 1e-2 * scale
+    assert _rel_l2(out, ref) <= 3e-3
+    # BN statistics are accumulated from the fp32 accumulators, before the bf16 rounding of the output
+    s1 = ref.sum(dim=(0, 2, 3))
+    s2 = (ref * ref).sum(dim=(0, 2, 3))
+    assert torch.allclose(stats[0].cpu(), s1, rtol=1e-3, atol=1e-3 * s2.sqrt().max().item())
+    assert torch.allclose(stats[1].cpu(), s2, rtol=1e-3)
+
+
+def test_conv_forward_addend(cuda_device):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = _bf16_round(torch.randn(2, 128, 16, 16, generator=g))
+    r = _bf16_round(torch.randn(2, 128, 16, 16, generator=g))
+    w = _bf16_round(torch.randn(128, 128, 1, 1, generator=g) * 0.1)
+    ref = F.conv2d(x, w) + r
+    y = ops.conv2d_igemm(ops.to_nhwc(x.to(cuda_device)), ops.pack_weight(w.to(cuda_device)), 128, 1,
+                         addend=ops.to_nhwc(r.to(cuda_device)))
+    out = ops.to_nchw(y).cpu()
+    assert _rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k", CASES)
+def test_conv_dgrad(cuda_device, N, H, W, cin, cout, k):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(99 + H + cin)
+    dy = _bf16_round(torch.randn(N, cout, H, W, generator=g))
+    w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cout * k * k) ** 0.5))
+    ref = torch.nn.grad.conv2d_input((N, cin, H, W), w, dy, padding=(k - 1) // 2)
+    wd = ops.pack_weight(w.to(cuda_device), mode=1)
+    dx = ops.conv2d_igemm(ops.to_nhwc(dy.to(cuda_device)), wd, cin, k)
+    out = ops.to_nchw(dx).cpu()
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert _rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k", CASES)
+def test_conv_wgrad(cuda_device, N, H, W, cin, cout, k):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(5 + H + cin)
+    x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
+    dy = _bf16_round(torch.randn(N, cout, H, W, generator=g))
+    ref = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, padding=(k - 1) // 2)
+    gw = ops.conv2d_wgrad(ops.to_nhwc(x.to(cuda_device)), ops.to_nhwc(dy.to(cuda_device)), cin, k).cpu()
+    # fp32 output, fp32 accumulation: only summation order differs
+    assert _rel_l2(gw, ref) <= 1e-4
+    assert (gw - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_head_conv(cuda_device):
+    """1x1 128->6 head writing the fp32 NCHW logits slice (hourglass.py:189-195, :237 torch.stack)."""
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = _bf16_round(torch.randn(2, 128, 32, 32, generator=g))
+    w = _bf16_round(torch.randn(6, 128, 1, 1, generator=g) * 0.1)
+    b = torch.randn(6, generator=g)
+    ref = F.conv2d(x, w, b)
+    logits = torch.zeros(2, 2, 6, 32, 32, device=cuda_device)
+    pad = torch.full((2, 32, 32, 64), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_igemm(ops.to_nhwc(x.to(cuda_device)), ops.pack_weight(w.to(cuda_device)), 6, 1,
+                     bias=b.to(cuda_device), head_out=logits, stack_idx=1, out2=pad)
+    out = logits.cpu()
+    assert torch.count_nonzero(out[:, 0]) == 0
+    assert torch.allclose(out[:, 1], ref, rtol=1e-4, atol=1e-4)
+    padc = ops.to_nchw(pad).cpu()
+    assert _rel_l2(padc[:, :6], ref) <= 3e-3
+    assert torch.count_nonzero(padc[:, 6:16]) == 0

@@ -1,0 +1,162 @@
+/* hd_b200.h — C ABI of libhd_b200.so, the B200-native (sm_100a) hot path of
+ * tyui592/Real_Time_Helmet_Detection.
+ *
+ * The reference has no FFI / plugin layer of its own: its boundary is a set of Python call signatures
+ * (hourglass.py:198-237 StackedHourglass, loss.py:6-40 LossCalculator, transform.py:73 hm2box,
+ * evaluate.py:114-182 Prediction). This header is the native boundary underneath our drop-in Python
+ * mirrors of those signatures; every entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - activations: NHWC bf16 ("nhwc"), channel count a multiple of 8; images / logits / targets: NCHW fp32;
+ *   - every call only ENQUEUES work on `stream`: no allocation, no synchronisation, no host read-back;
+ *     outputs and workspaces are allocated by the caller (torch caching allocator in the Python host);
+ *   - return value 0 on success, negative errno-style code otherwise (-22 invalid argument, -5 CUDA error,
+ *     -38 unsupported); hd_last_error() returns a thread-local message for the last failure;
+ *   - there is no CPU fallback: without a CUDA device the compute entry points fail with -5.
+ */
+#ifndef HD_B200_H
+#define HD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* hd_stream_t; /* == cudaStream_t */
+
+const char* hd_last_error(void);
+int hd_version(void);
+
+/* ------------------------------------------------------------------ convolutions (hourglass.py:94-108) */
+
+/* Implicit-GEMM conv, stride 1, "same" padding, on tcgen05 tensor cores. Replaces nn.Conv2d (hourglass.py:100)
+ * forward for the 3x3 / 1x1 convs and, with mode-1 packed weights, its input gradient (dgrad).
+ *   x        nhwc [N,H,W,cin], cin % 64 == 0
+ *   w_packed bf16 [ksize*ksize][block_n][cin] from hd_pack_conv_weight / hd_stem_pack_weight
+ *   out      out_mode 0: nhwc bf16, channel stride out_cs ; out_mode 1 (block_n 16 only): fp32 NCHW slice
+ *            [:, stack_idx] of a (N, num_stack, cout, H, W) logits tensor (hourglass.py:237 torch.stack)
+ *   out2     optional (block_n 16): second nhwc bf16 copy, channel stride out2_cs, channels [cout,16) zeroed
+ *   bias     optional fp32 [cout] ; addend optional nhwc bf16 like `out` (fused residual / merge add, :235)
+ *   stat_sum / stat_sqsum  optional fp32 [cout]: per-channel sum / sum of squares of the fp32 result are
+ *            ACCUMULATED (train-mode BatchNorm statistics, hourglass.py:103)
+ *   block_n  128, 64 or 16 (>= cout) */
+int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                    const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
+                    int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
+                    hd_stream_t stream);
+
+/* Weight gradient of the same convs (autograd of hourglass.py:100): grad_w (OIHW fp32 [cout][cin_real][k][k])
+ * = (accumulate ? grad_w : 0) + sum_pixels dy[p, co] * x[p + tap, ci].  x nhwc [.., cin], dy nhwc [.., cout],
+ * cout in {64,128}, cin in {64,128,192(k=1)}. workspace: hd_conv2d_wgrad_workspace_bytes() bytes.
+ * stem_perm: K index is the stem im2col order, grad_w is [cout][3][7][7] (hourglass.py:163). */
+int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W, int cin,
+                    int cin_real, int cout, int ksize, int accumulate, int stem_perm, hd_stream_t stream);
+int hd_conv2d_wgrad_ksplit(int N, int H, int W, int ksize);
+size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int ksize);
+
+/* OIHW fp32 -> packed bf16 UMMA operand. mode 0: forward [tap][co][ci]; mode 1: dgrad [tap'][ci][co] (rotated). */
+int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int ksize, int rows_pad, int k_pad,
+                        int mode, hd_stream_t stream);
+int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int c_pad, hd_stream_t stream);
+int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, int c_stride, hd_stream_t stream);
+
+/* 7x7 stride-2 stem (hourglass.py:163): image (N,3,H,W) fp32 -> patch matrix nhwc [N,H/2,W/2,192] (K = 147 padded),
+ * then hd_conv2d_igemm(cin=192, ksize=1) with weights from hd_stem_pack_weight ([1][64][192]). */
+int hd_stem_im2col(const float* x, void* patches, int N, int H, int W, hd_stream_t stream);
+int hd_stem_pack_weight(const float* w, void* out, int cout, hd_stream_t stream);
+
+/* Backward of the 1x1 prediction head (hourglass.py:189-195). dw/dbias are accumulated into. */
+int hd_head_backward(const float* dlogits, long long batch_stride, const void* extra, int extra_cs, const void* feat,
+                     const void* w_packed, void* dfeat, float* dw, float* dbias, int N, int H, int W, int cout,
+                     hd_stream_t stream);
+
+/* ------------------------------------------------------------------ BatchNorm / activation / pooling */
+
+/* nn.BatchNorm2d (hourglass.py:103) finalize: statistics -> scale/shift (+ running-stat update in training). */
+int hd_bn_finalize(const float* sum, const float* sqsum, float count, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                   int training, float* scale, float* shift, float* save_mean, float* save_rstd, int C,
+                   hd_stream_t stream);
+/* z = act(y*scale + shift)  (Convolution.forward, hourglass.py:107-108) */
+int hd_bn_act(const void* y, const float* scale, const float* shift, void* z, long long npix, int C, int relu,
+              hd_stream_t stream);
+/* out = relu(y2*s2 + b2 + skip) with skip = x or ys*ss + bs  (Residual.forward, hourglass.py:125-127) */
+int hd_bn_add_relu(const void* y2, const float* s2, const float* b2, const void* skip, const float* ss,
+                   const float* bs, void* out, long long npix, int C, hd_stream_t stream);
+int hd_maxpool2(const void* x, void* y, int N, int H, int W, int C, hd_stream_t stream);           /* :72  */
+int hd_upsample2_add(const void* up1, const void* low, void* out, int N, int H, int W, int C,
+                     hd_stream_t stream);                                                         /* :147,:156 */
+/* backward counterparts */
+int hd_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
+                     const void* ys, const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
+                     hd_stream_t stream);
+int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
+                       const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
+                       hd_stream_t stream);
+int hd_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy, const void* ys,
+                    const float* coef_s, void* dys, void* gout, long long npix, int C, hd_stream_t stream);
+int hd_maxpool2_bwd(const void* x, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
+                    int W, int C, hd_stream_t stream);
+int hd_sum2x2(const void* dout, void* dlow, int N, int H, int W, int C, hd_stream_t stream);
+int hd_add(const void* a, const void* b, const void* c, void* out, long long nelem, hd_stream_t stream);
+int hd_colsum(const void* x, float* out, long long npix, int C, int cs, hd_stream_t stream);
+
+/* ------------------------------------------------------------------ losses (loss.py:6-69, train.py:105-120) */
+
+/* Fused focal + masked-L1 loss. hm/off/size: fp32 (B,C|2|2,H,W) views with dense planes and batch strides *_bs.
+ * out[0..4] = hm, offset, size, total, 1/(B*num_pos). from_logits: sigmoid(hm) inside; sigmoid_reg: sigmoid(off/size). */
+int hd_loss_forward(const float* hm, long long hm_bs, const float* off, long long off_bs, const float* size,
+                    long long size_bs, const float* ghm, const float* goff, const float* gsize, const float* gmask,
+                    int B, int C, int H, int W, float alpha, float beta, float w_hm, float w_off, float w_size,
+                    int from_logits, int sigmoid_reg, float* sums, float* out, hd_stream_t stream);
+int hd_loss_backward(const float* hm, long long hm_bs, const float* off, long long off_bs, const float* size,
+                     long long size_bs, const float* ghm, const float* goff, const float* gsize, const float* gmask,
+                     int B, int C, int H, int W, float alpha, float beta, float w_hm, float w_off, float w_size,
+                     int from_logits, int sigmoid_reg, const float* fwd_out, const float* grad_out, float* d_hm,
+                     long long d_hm_bs, float* d_off, long long d_off_bs, float* d_size, long long d_size_bs,
+                     hd_stream_t stream);
+
+/* ------------------------------------------------------------------ decode (transform.py:73-110, evaluate.py:126-182) */
+
+size_t hd_decode_scratch_bytes(int B, int C, int H, int W);
+/* One CTA per image: per stack sigmoid (apply_sigmoid) + 3x3 peak test + joint top-k + gather + boxes + threshold,
+ * then (do_nms) class-agnostic hard NMS over the concatenated stacks. heat/off/wh: fp32 planes with batch/stack
+ * strides. Outputs: boxes [B][S*topk][4] fp32, cls [B][S*topk] int64, scores [B][S*topk] fp32, count [B] int32. */
+int hd_decode_nms(const float* heat, long long bs_heat, long long ss_heat, const float* off, long long bs_off,
+                  long long ss_off, const float* wh, long long bs_wh, long long ss_wh, int B, int S, int C, int H,
+                  int W, int topk, float scale_factor, float conf_th, float nms_th, int normalized,
+                  int apply_sigmoid, int do_nms, void* scratch, float* out_boxes, long long* out_cls,
+                  float* out_scores, int* out_count, hd_stream_t stream);
+
+/* ------------------------------------------------------------------ whole-network executor (hourglass.py:198-237) */
+
+/* Pointers of one `Convolution` module (hourglass.py:94-108): parameters, buffers and gradient destinations.
+ * Unused members are NULL. Gradient destinations must be zero-initialised by the caller before hd_net_backward. */
+typedef struct hd_unit_ptrs {
+    float* w;      float* b;                       /* convolution.weight (OIHW fp32), convolution.bias */
+    float* gamma;  float* beta;                    /* bn.weight, bn.bias */
+    float* running_mean; float* running_var; long long* num_batches_tracked;
+    float* dw;     float* db;   float* dgamma;  float* dbeta;
+} hd_unit_ptrs;
+
+typedef struct hd_net hd_net;
+/* num_stack, in_ch (128) and out_ch (= num_cls + 4) of StackedHourglass.__init__ (hourglass.py:199). */
+int hd_net_create(int num_stack, int in_ch, int out_ch, hd_net** net);
+void hd_net_destroy(hd_net* net);
+int hd_net_num_units(const hd_net* net);
+/* Bytes of workspace hd_net_forward (+ hd_net_backward when with_backward) need for a (B,3,H,W) input. */
+size_t hd_net_workspace_bytes(hd_net* net, int B, int H, int W, int with_backward);
+/* StackedHourglass.forward (hourglass.py:223-237): x (B,3,H,W) fp32 -> logits (B,S,out_ch,H/4,W/4) fp32.
+ * training: batch statistics + running-stat update and activations kept for hd_net_backward. */
+int hd_net_forward(hd_net* net, const hd_unit_ptrs* units, int n_units, const float* x, float* logits,
+                   void* workspace, size_t workspace_bytes, int B, int H, int W, int training, hd_stream_t stream);
+/* Autograd of the above: dlogits (B,S,out_ch,H/4,W/4) fp32 -> all parameter gradients (units[i].d*). */
+int hd_net_backward(hd_net* net, const hd_unit_ptrs* units, int n_units, const float* dlogits, void* workspace,
+                    size_t workspace_bytes, hd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HD_B200_H */

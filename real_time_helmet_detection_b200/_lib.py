@@ -18,18 +18,39 @@ _lib = None
 P = c_void_p
 I = c_int
 F = c_float
+LL = c_longlong
 
 # name -> (restype, argtypes)
 _SIGNATURES = {
     "hd_last_error": (c_char_p, []),
     "hd_version": (I, []),
     "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
-    "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_wgrad_ksplit": (I, [I, I, I, I]),
     "hd_conv2d_wgrad_workspace_bytes": (c_size_t, [I, I, I, I, I]),
     "hd_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, P]),
     "hd_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, I, P]),
     "hd_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, I, P]),
+    "hd_stem_im2col": (I, [P, P, I, I, I, P]),
+    "hd_stem_pack_weight": (I, [P, P, I, P]),
+    "hd_head_backward": (I, [P, LL, P, I, P, P, P, P, P, I, I, I, I, P]),
+    "hd_bn_finalize": (I, [P, P, F, P, P, P, P, P, F, F, I, P, P, P, P, I, P]),
+    "hd_bn_act": (I, [P, P, P, P, LL, I, I, P]),
+    "hd_bn_add_relu": (I, [P, P, P, P, P, P, P, LL, I, P]),
+    "hd_maxpool2": (I, [P, P, I, I, I, I, P]),
+    "hd_upsample2_add": (I, [P, P, P, I, I, I, I, P]),
+    "hd_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, P, P, LL, I, P]),
+    "hd_bn_bwd_finalize": (I, [P, P, F, P, P, P, P, P, P, I, I, P]),
+    "hd_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, LL, I, P]),
+    "hd_maxpool2_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
+    "hd_sum2x2": (I, [P, P, I, I, I, I, P]),
+    "hd_add": (I, [P, P, P, P, LL, P]),
+    "hd_colsum": (I, [P, P, LL, I, I, P]),
+    "hd_loss_forward": (I, [P, LL, P, LL, P, LL, P, P, P, P, I, I, I, I, F, F, F, F, F, I, I, P, P, P]),
+    "hd_loss_backward": (I, [P, LL, P, LL, P, LL, P, P, P, P, I, I, I, I, F, F, F, F, F, I, I, P, P,
+                             P, LL, P, LL, P, LL, P]),
+    "hd_decode_scratch_bytes": (c_size_t, [I, I, I, I]),
+    "hd_decode_nms": (I, [P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, I, I, I, F, F, F, I, I, I, P, P, P, P, P, P]),
 }
 
 

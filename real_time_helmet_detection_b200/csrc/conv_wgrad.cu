@@ -20,7 +20,6 @@
 namespace hd {
 
 constexpr int kWgThreads = 256;
-constexpr int kWgBStages = 4;
 constexpr int kWgABytes = 2 * 128 * 128;  // dY tile: 128 pixels x 128 cout (two 64-channel atoms)
 
 struct WgradParams {
@@ -41,6 +40,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                   const WgradParams p) {
     constexpr int kBBytes = 128 * BLOCK_N * 2;
     constexpr int kNChunks = BLOCK_N / 64;
+    constexpr int kWgBStages = BLOCK_N > 128 ? 3 : 4;
     constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 1, 1);
 
     extern __shared__ uint8_t smem_raw[];
@@ -171,8 +171,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 }
 
 // grad[co][ci][tap] (+)= sum_s ws[s][tap][co][ci_pad]   (OIHW fp32, the layout of nn.Conv2d.weight.grad)
+// stem_perm: the GEMM K index of the 7x7 stem is k = (ky*7 + kx)*3 + c (im2col order, stem.cu); scatter it
+// back to the OIHW position [co][c][ky][kx].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int ksplit, int taps,
-                                    int cout, int cin, int rows_pad, int cin_pad, int accumulate) {
+                                    int cout, int cin, int rows_pad, int cin_pad, int accumulate, int stem_perm) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * cout * cin, ci fastest
     const int total = taps * cout * cin;
     if (idx >= total) return;
@@ -184,11 +186,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     const float* src = ws + (static_cast<size_t>(tap) * rows_pad + co) * cin_pad + ci;
     for (int k = 0; k < ksplit; ++k) s += src[k * stride];
     float* g = grad + (static_cast<size_t>(co) * cin + ci) * taps + tap;
+    if (stem_perm) {
+        const int c = ci % 3, kk = ci / 3;   // kk = ky*7 + kx
+        g = grad + (static_cast<size_t>(co) * 3 + c) * 49 + kk;
+    }
     *g = accumulate ? (*g + s) : s;
 }
 
 template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
+    constexpr int kWgBStages = BLOCK_N > 128 ? 3 : 4;
     constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * 128 * BLOCK_N * 2 + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
@@ -223,10 +230,13 @@ extern "C" size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, 
 
 // See include/hd_b200.h.
 extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W,
-                               int cin, int cin_real, int cout, int ksize, int accumulate, cudaStream_t stream) {
+                               int cin, int cin_real, int cout, int ksize, int accumulate, int stem_perm,
+                               cudaStream_t stream) {
     using namespace hd;
-    HD_REQUIRE(cout == 128, "conv_wgrad: cout=%d (tensor-core path needs 128)", cout);
-    HD_REQUIRE(cin == 64 || cin == 128, "conv_wgrad: cin=%d unsupported", cin);
+    // cout == 64: the second 64-channel atom of the dY tile is fetched out of bounds and zero-filled by TMA.
+    HD_REQUIRE(cout == 128 || cout == 64, "conv_wgrad: cout=%d (tensor-core path needs 64 or 128)", cout);
+    HD_REQUIRE(cin == 64 || cin == 128 || (cin == 192 && ksize == 1), "conv_wgrad: cin=%d unsupported", cin);
+    HD_REQUIRE(!stem_perm || (cin == 192 && cin_real == 147 && ksize == 1), "conv_wgrad: stem_perm needs K=147/192");
     HD_REQUIRE(cin_real >= 1 && cin_real <= cin, "conv_wgrad: cin_real=%d", cin_real);
     HD_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize=%d unsupported", ksize);
     HD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_wgrad: empty tensor");
@@ -260,11 +270,13 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
         int rc = make_tmap_bf16(&tx, x, 4, dims, str, box);
         if (rc) return rc;
     }
-    int rc = (cin == 128) ? launch_wgrad<128>(tdy, tx, p, stream) : launch_wgrad<64>(tdy, tx, p, stream);
+    int rc = (cin == 192)   ? launch_wgrad<192>(tdy, tx, p, stream)
+             : (cin == 128) ? launch_wgrad<128>(tdy, tx, p, stream)
+                            : launch_wgrad<64>(tdy, tx, p, stream);
     if (rc) return rc;
     const int total = p.taps * cout * cin_real;
     wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128,
-                                                                 cin, accumulate);
+                                                                 cin, accumulate, stem_perm);
     HD_CHECK_CUDA(cudaGetLastError());
     return HD_OK;
 }

@@ -1,0 +1,564 @@
+// HBM-bound elementwise / reduction kernels around the convolutions, all on NHWC bf16 activations with
+// 16-byte (8-channel) vector accesses and fp32 math:
+//   * train/eval BatchNorm finalize (hourglass.py:103 nn.BatchNorm2d: eps 1e-5, momentum 0.1, biased var to
+//     normalise, unbiased var into running_var), BN+activation apply, residual tail relu(bn(y2) + skip)
+//     (hourglass.py:125-127), 2x2 max-pool (:72), nearest-upsample + add (:147,:155-156);
+//   * their backward counterparts (the autograd graph PyTorch would build for those modules).
+// Per-channel BN statistics themselves are produced by the conv epilogue (conv_igemm.cu).
+#include <cuda_bf16.h>
+
+#include "hd_common.h"
+
+namespace hd {
+
+struct F8 {
+    float v[8];
+};
+
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    F8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+static inline int grid_for(size_t work, int block, int max_blocks) {
+    size_t g = (work + block - 1) / block;
+    if (g > (size_t)max_blocks) g = max_blocks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------- BN finalize
+// bnp layout per BN layer (fp32, 6*C): scale | shift | mean | rstd | (unused) | (unused)
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
+                                   int training, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    float mean, var;
+    if (training) {
+        mean = sum[c] / count;
+        var = fmaxf(sqsum[c] / count - mean * mean, 0.f);
+        if (running_mean) {
+            const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    save_mean[c] = mean;
+    save_rstd[c] = rstd;
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+// z = act(y * scale + shift)
+template <bool RELU>
+__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, __nv_bfloat16* __restrict__ z, size_t nvec, int C) {
+    __shared__ float s_sc[256], s_sh[256];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        s_sc[i] = scale[i];
+        s_sh[i] = shift[i];
+    }
+    __syncthreads();
+    const int cvec = C >> 3;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % cvec) << 3;
+        F8 a = load8(y + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = fmaf(a.v[j], s_sc[c0 + j], s_sh[c0 + j]);
+            a.v[j] = RELU ? fmaxf(t, 0.f) : t;
+        }
+        store8(z + i * 8, a);
+    }
+}
+
+// out = relu(y2 * s2 + b2 + skip), skip = x (identity) or ys * ss + bs (1x1 conv + BN)
+template <bool SKIP_BN>
+__global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ s2,
+                                   const float* __restrict__ b2, const __nv_bfloat16* __restrict__ skip,
+                                   const float* __restrict__ ss, const float* __restrict__ bs,
+                                   __nv_bfloat16* __restrict__ out, size_t nvec, int C) {
+    __shared__ float p[4][256];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        p[0][i] = s2[i];
+        p[1][i] = b2[i];
+        p[2][i] = SKIP_BN ? ss[i] : 1.f;
+        p[3][i] = SKIP_BN ? bs[i] : 0.f;
+    }
+    __syncthreads();
+    const int cvec = C >> 3;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % cvec) << 3;
+        F8 a = load8(y2 + i * 8);
+        F8 k = load8(skip + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = fmaf(a.v[j], p[0][c0 + j], p[1][c0 + j]);
+            float s = SKIP_BN ? fmaf(k.v[j], p[2][c0 + j], p[3][c0 + j]) : k.v[j];
+            a.v[j] = fmaxf(t + s, 0.f);
+        }
+        store8(out + i * 8, a);
+    }
+}
+
+// 2x2 max pool, stride 2 (H, W even)
+__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                int W, int C) {
+    const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % cvec;
+        size_t pix = i / cvec;
+        const int ox = pix % Wo;
+        const int oy = (pix / Wo) % Ho;
+        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+        const __nv_bfloat16* base = x + ((static_cast<size_t>(n) * H + 2 * oy) * W + 2 * ox) * C + cv * 8;
+        F8 a = load8(base), b = load8(base + C), c = load8(base + static_cast<size_t>(W) * C),
+           d = load8(base + static_cast<size_t>(W) * C + C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.v[j] = fmaxf(fmaxf(a.v[j], b.v[j]), fmaxf(c.v[j], d.v[j]));
+        store8(y + i * 8, a);
+    }
+}
+
+// out[n,y,x,:] = up1[n,y,x,:] + low[n,y/2,x/2,:]   (nearest x2 upsample + add); H, W are the OUTPUT sizes
+__global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low,
+                                    __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+    const int cvec = C >> 3;
+    const size_t nvec = static_cast<size_t>(N) * H * W * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % cvec;
+        size_t pix = i / cvec;
+        const int x = pix % W;
+        const int y = (pix / W) % H;
+        const int n = pix / (static_cast<size_t>(W) * H);
+        F8 a = load8(up1 + i * 8);
+        F8 b = load8(low + ((static_cast<size_t>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * C + cv * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.v[j] += b.v[j];
+        store8(out + i * 8, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+// Per-channel reductions for BN backward behind a ReLU:  g = dout * (out > 0)
+//   sums[0][c] += sum g ; sums[1][c] += sum g * yhat(y) ; sums[2][c] += sum g * yhat(ys)   (ys optional)
+// yhat = (y - mean) * rstd.
+template <bool SECOND>
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ ys,
+                                     const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
+                                     float* __restrict__ sums, size_t npix, int C) {
+    extern __shared__ float red[];  // [3][blockDim.x/cvec rows][C]  -> reduced over rows
+    const int cvec = C >> 3;
+    const int lane_c = threadIdx.x % cvec;          // which 8-channel vector
+    const int row = threadIdx.x / cvec;             // pixel lane inside the block
+    const int rows = blockDim.x / cvec;
+    const int c0 = lane_c << 3;
+    float m[8], r[8], ms[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        m[j] = mean[c0 + j];
+        r[j] = rstd[c0 + j];
+        ms[j] = SECOND ? mean_s[c0 + j] : 0.f;
+        rs[j] = SECOND ? rstd_s[c0 + j] : 0.f;
+    }
+    float a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = a2[j] = 0.f;
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + row; pix < npix;
+         pix += static_cast<size_t>(gridDim.x) * rows) {
+        const size_t off = pix * C + c0;
+        F8 g = load8(dout + off);
+        F8 o = load8(out + off);
+        F8 yy = load8(y + off);
+        F8 y2;
+        if (SECOND) y2 = load8(ys + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
+            a0[j] += gj;
+            a1[j] += gj * ((yy.v[j] - m[j]) * r[j]);
+            if (SECOND) a2[j] += gj * ((y2.v[j] - ms[j]) * rs[j]);
+        }
+    }
+    float* r0 = red;
+    float* r1 = red + rows * C;
+    float* r2 = red + 2 * rows * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        r0[row * C + c0 + j] = a0[j];
+        r1[row * C + c0 + j] = a1[j];
+        if (SECOND) r2[row * C + c0 + j] = a2[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < rows; ++k) {
+            s0 += r0[k * C + c];
+            s1 += r1[k * C + c];
+            if (SECOND) s2 += r2[k * C + c];
+        }
+        atomicAdd(sums + c, s0);
+        atomicAdd(sums + C + c, s1);
+        if (SECOND) atomicAdd(sums + 2 * C + c, s2);
+    }
+}
+
+// From the reduction sums build the per-channel affine form of the BN input gradient
+//   dy = a * g + b * y + c      with  a = gamma*rstd, b = -gamma*rstd^2*S1/M, c = gamma*rstd*(mean*rstd*S1 - S0)/M
+// and the parameter gradients dgamma = S1, dbeta = S0 (accumulated when `accumulate`).
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float* __restrict__ s1, float count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* __restrict__ coef,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float g = gamma[c], r = rstd[c], m = mean[c];
+    const float S0 = s0[c], S1 = s1[c];
+    coef[c] = g * r;
+    coef[C + c] = -g * r * r * S1 / count;
+    coef[2 * C + c] = g * r * (m * r * S1 - S0) / count;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + S1 : S1;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + S0 : S0;
+}
+
+// g = dout * (out > 0);  dy = a*g + b*y + c ; optionally dys = as*g + bs*ys + cs ; optionally gout = g
+template <bool SECOND, bool WRITE_G>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
+                                    __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
+                                    const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
+                                    __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
+    __shared__ float p[6][256];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        p[0][i] = coef[i];
+        p[1][i] = coef[C + i];
+        p[2][i] = coef[2 * C + i];
+        if (SECOND) {
+            p[3][i] = coef_s[i];
+            p[4][i] = coef_s[C + i];
+            p[5][i] = coef_s[2 * C + i];
+        }
+    }
+    __syncthreads();
+    const int cvec = C >> 3;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % cvec) << 3;
+        F8 g = load8(dout + i * 8);
+        F8 o = load8(out + i * 8);
+        F8 yy = load8(y + i * 8);
+        F8 r, r2, y2;
+        if (SECOND) y2 = load8(ys + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
+            g.v[j] = gj;
+            r.v[j] = fmaf(p[0][c0 + j], gj, fmaf(p[1][c0 + j], yy.v[j], p[2][c0 + j]));
+            if (SECOND) r2.v[j] = fmaf(p[3][c0 + j], gj, fmaf(p[4][c0 + j], y2.v[j], p[5][c0 + j]));
+        }
+        store8(dy + i * 8, r);
+        if (SECOND) store8(dys + i * 8, r2);
+        if (WRITE_G) store8(gout + i * 8, g);
+    }
+}
+
+// dx = route(dpool) [+ add1] [+ add2]; the pooled gradient goes to the first maximum of each 2x2 window in
+// row-major scan order (PyTorch max_pool2d backward semantics).
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dpool,
+                                    const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
+                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+    const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % cvec;
+        size_t pix = i / cvec;
+        const int ox = pix % Wo;
+        const int oy = (pix / Wo) % Ho;
+        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+        const size_t o00 = ((static_cast<size_t>(n) * H + 2 * oy) * W + 2 * ox) * C + cv * 8;
+        const size_t offs[4] = {o00, o00 + C, o00 + static_cast<size_t>(W) * C, o00 + static_cast<size_t>(W) * C + C};
+        F8 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = load8(x + offs[k]);
+        F8 g = load8(dpool + i * 8);
+        F8 r[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int best = 0;
+            float bv = v[0].v[j];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (v[k].v[j] > bv) { bv = v[k].v[j]; best = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k].v[j] = (k == best) ? g.v[j] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (add1) {
+                F8 a = load8(add1 + offs[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[k].v[j] += a.v[j];
+            }
+            if (add2) {
+                F8 a = load8(add2 + offs[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[k].v[j] += a.v[j];
+            }
+            store8(dx + offs[k], r[k]);
+        }
+    }
+}
+
+// dlow[n,y,x,:] = sum of the 2x2 block of dout (backward of nearest x2 upsample); H, W are dout's sizes
+__global__ void sum2x2_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dlow, int N, int H,
+                              int W, int C) {
+    const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % cvec;
+        size_t pix = i / cvec;
+        const int ox = pix % Wo;
+        const int oy = (pix / Wo) % Ho;
+        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+        const __nv_bfloat16* base = dout + ((static_cast<size_t>(n) * H + 2 * oy) * W + 2 * ox) * C + cv * 8;
+        F8 a = load8(base), b = load8(base + C), c = load8(base + static_cast<size_t>(W) * C),
+           d = load8(base + static_cast<size_t>(W) * C + C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.v[j] = (a.v[j] + b.v[j]) + (c.v[j] + d.v[j]);
+        store8(dlow + i * 8, a);
+    }
+}
+
+// out = a + b (+ c)
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, size_t nvec) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        F8 x = load8(a + i * 8), y = load8(b + i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x.v[j] += y.v[j];
+        if (c) {
+            F8 z = load8(c + i * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x.v[j] += z.v[j];
+        }
+        store8(out + i * 8, x);
+    }
+}
+
+// out[c] (+)= sum over pixels of x[pix, c]   (bias gradients)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, size_t npix, int C,
+                              int cs) {
+    extern __shared__ float red[];
+    const int cvec = C >> 3;
+    const int lane_c = threadIdx.x % cvec, row = threadIdx.x / cvec, rows = blockDim.x / cvec;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + row; pix < npix;
+         pix += static_cast<size_t>(gridDim.x) * rows) {
+        F8 v = load8(x + pix * cs + lane_c * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += v.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[row * C + lane_c * 8 + j] = a[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < rows; ++k) s += red[k * C + c];
+        atomicAdd(out + c, s);
+    }
+}
+
+}  // namespace hd
+
+using namespace hd;
+typedef const void* cvp;
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+static inline int ew_blocks(size_t nvec) { return grid_for(nvec, 256, sm_count() * 16); }
+
+extern "C" int hd_bn_finalize(const float* sum, const float* sqsum, float count, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var,
+                              long long* num_batches_tracked, float momentum, float eps, int training, float* scale,
+                              float* shift, float* save_mean, float* save_rstd, int C, cudaStream_t stream) {
+    HD_REQUIRE(C > 0 && C <= 256, "bn_finalize: C=%d", C);
+    HD_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
+                                                          num_batches_tracked, momentum, eps, training, scale, shift,
+                                                          save_mean, save_rstd, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z, long long npix, int C, int relu,
+                         cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_act: C=%d", C);
+    const size_t nvec = static_cast<size_t>(npix) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    if (relu)
+        bn_act_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
+    else
+        bn_act_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_bn_add_relu(cvp y2, const float* s2, const float* b2, cvp skip, const float* ss, const float* bs,
+                              void* out, long long npix, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_add_relu: C=%d", C);
+    HD_REQUIRE((ss == nullptr) == (bs == nullptr), "bn_add_relu: skip scale/shift must come in pairs");
+    const size_t nvec = static_cast<size_t>(npix) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    if (ss)
+        bn_add_relu_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
+    else
+        bn_add_relu_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_maxpool2(cvp x, void* y, int N, int H, int W, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: shape (%d,%d,%d,%d)", N, H, W, C);
+    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    maxpool2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BFW(y), N, H, W, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "upsample2_add: shape (%d,%d,%d,%d)", N, H, W, C);
+    const size_t nvec = static_cast<size_t>(N) * H * W * (C / 8);
+    if (nvec == 0) return HD_OK;
+    upsample_add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(up1), BF(low), BFW(out), N, H, W, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, cvp y, const float* mean, const float* rstd, cvp ys,
+                                const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
+                                cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
+    if (npix == 0) return HD_OK;
+    const int rows = 256 / (C / 8);
+    const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
+    const size_t smem = 3 * static_cast<size_t>(rows) * C * sizeof(float);
+    if (ys) {
+        static bool set1 = false;
+        if (!set1) { HD_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); set1 = true; }
+        bn_bwd_reduce_kernel<true><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, BF(ys), mean_s,
+                                                                rstd_s, sums, static_cast<size_t>(npix), C);
+    } else {
+        static bool set0 = false;
+        if (!set0) { HD_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); set0 = true; }
+        bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, nullptr,
+                                                                 nullptr, nullptr, sums, static_cast<size_t>(npix), C);
+    }
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma,
+                                  const float* mean, const float* rstd, float* coef, float* dgamma, float* dbeta,
+                                  int accumulate, int C, cudaStream_t stream) {
+    HD_REQUIRE(C > 0 && C <= 256, "bn_bwd_finalize: C=%d", C);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(s0, s1, count, gamma, mean, rstd, coef, dgamma, dbeta,
+                                                              accumulate, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, cvp y, const float* coef, void* dy, cvp ys, const float* coef_s,
+                               void* dys, void* gout, long long npix, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_bwd_apply: C=%d", C);
+    const size_t nvec = static_cast<size_t>(npix) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    const int blocks = ew_blocks(nvec);
+    if (ys && gout)
+        bn_bwd_apply_kernel<true, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C);
+    else if (ys)
+        bn_bwd_apply_kernel<true, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C);
+    else if (gout)
+        bn_bwd_apply_kernel<false, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C);
+    else
+        bn_bwd_apply_kernel<false, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_maxpool2_bwd(cvp x, cvp dpool, cvp add1, cvp add2, void* dx, int N, int H, int W, int C,
+                               cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: shape (%d,%d,%d,%d)", N, H, W, C);
+    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    maxpool2_bwd_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_sum2x2(cvp dout, void* dlow, int N, int H, int W, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "sum2x2: shape (%d,%d,%d,%d)", N, H, W, C);
+    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    sum2x2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(dout), BFW(dlow), N, H, W, C);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_add(cvp a, cvp b, cvp c, void* out, long long nelem, cudaStream_t stream) {
+    HD_REQUIRE(nelem % 8 == 0, "add: nelem %% 8 != 0");
+    const size_t nvec = static_cast<size_t>(nelem) / 8;
+    if (nvec == 0) return HD_OK;
+    add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(a), BF(b), BF(c), BFW(out), nvec);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && cs >= C, "colsum: C=%d cs=%d", C, cs);
+    if (npix == 0) return HD_OK;
+    const int rows = 256 / (C / 8);
+    const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
+    colsum_kernel<<<blocks, 256, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(BF(x), out, static_cast<size_t>(npix), C, cs);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -1,0 +1,118 @@
+// Backward of the 1x1 prediction head (hourglass.py:189-195: conv 128 -> num_cls+4, bias, linear).
+// cout = 6 is far below a UMMA tile, and the op is HBM-bound (reads the 128-channel feature map once), so this is
+// a fused SIMT kernel:   g = dlogits (+ extra) ;  dfeat[p, k] = sum_c g[p, c] * W[c, k] ;
+//                        dW[c, k] += sum_p g[p, c] * feat[p, k] ;  dbias[c] += sum_p g[p, c].
+#include <cuda_bf16.h>
+
+#include "hd_common.h"
+
+namespace hd {
+
+constexpr int kHeadMaxC = 16;
+
+__global__ void head_bwd_kernel(const float* __restrict__ dlogits, long long bs, int HW, int cout,
+                                const __nv_bfloat16* __restrict__ extra, int extra_cs,
+                                const __nv_bfloat16* __restrict__ feat, const __nv_bfloat16* __restrict__ wp,
+                                __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ dbias,
+                                long long npix) {
+    // 16 lanes per pixel, 8 feature channels each (128 channels); blockDim = 256 -> 16 pixels per pass
+    __shared__ float s_w[kHeadMaxC][128];
+    __shared__ float s_red[16][kHeadMaxC * 8 + 1];
+    for (int i = threadIdx.x; i < cout * 128; i += blockDim.x) s_w[i / 128][i % 128] = __bfloat162float(wp[i]);
+    __syncthreads();
+    const int lane_c = threadIdx.x & 15, row = threadIdx.x >> 4;
+    const int k0 = lane_c * 8;
+    float acc[kHeadMaxC][8];
+    float accb[kHeadMaxC];
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) {
+        accb[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+    }
+    for (long long pix = static_cast<long long>(blockIdx.x) * 16 + row; pix < npix;
+         pix += static_cast<long long>(gridDim.x) * 16) {
+        const long long n = pix / HW, p = pix - n * HW;
+        uint4 u = *reinterpret_cast<const uint4*>(feat + pix * 128 + k0);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 t = __bfloat1622float2(h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHeadMaxC; ++c) {
+            if (c < cout) {
+                float g = dlogits[n * bs + static_cast<long long>(c) * HW + p];
+                if (extra) g += __bfloat162float(extra[pix * extra_cs + c]);
+                accb[c] += g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    d[j] = fmaf(g, s_w[c][k0 + j], d[j]);
+                    acc[c][j] = fmaf(g, f[j], acc[c][j]);
+                }
+            }
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+        *reinterpret_cast<uint4*>(dfeat + pix * 128 + k0) = o;
+    }
+    // reduce the 16 pixel rows of the block, one channel-vector (lane_c) at a time
+    for (int lc = 0; lc < 16; ++lc) {
+        __syncthreads();
+        if (lane_c == lc) {
+#pragma unroll
+            for (int c = 0; c < kHeadMaxC; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_red[row][c * 8 + j] = acc[c][j];
+        }
+        __syncthreads();
+        if (threadIdx.x < cout * 8) {
+            float s = 0.f;
+            for (int r = 0; r < 16; ++r) s += s_red[r][threadIdx.x];
+            const int c = threadIdx.x >> 3, j = threadIdx.x & 7;
+            atomicAdd(dw + c * 128 + lc * 8 + j, s);
+        }
+    }
+    __syncthreads();
+    if (lane_c == 0) {
+#pragma unroll
+        for (int c = 0; c < kHeadMaxC; ++c) s_red[row][c] = accb[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < cout) {
+        float s = 0.f;
+        for (int r = 0; r < 16; ++r) s += s_red[r][threadIdx.x];
+        atomicAdd(dbias + threadIdx.x, s);
+    }
+}
+
+}  // namespace hd
+
+// dlogits: fp32 NCHW slice with batch stride `bs` (elements) and channel stride H*W; feat/dfeat: NHWC bf16 (128 ch);
+// wp: packed forward weights [>=cout][128] bf16; dw [cout][128] and dbias [cout] are ACCUMULATED into.
+extern "C" int hd_head_backward(const float* dlogits, long long bs, const void* extra, int extra_cs, const void* feat,
+                                const void* wp, void* dfeat, float* dw, float* dbias, int N, int H, int W, int cout,
+                                cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(cout >= 1 && cout <= kHeadMaxC, "head_backward: cout=%d", cout);
+    HD_REQUIRE(N > 0 && H > 0 && W > 0, "head_backward: empty tensor");
+    const long long npix = static_cast<long long>(N) * H * W;
+    long long g = (npix + 63) / 64;
+    const long long cap = static_cast<long long>(sm_count()) * 4;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    head_bwd_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(
+        dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+        reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
+        reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+    HD_CHECK_CUDA(cudaGetLastError());
+    return HD_OK;
+}

@@ -1,0 +1,170 @@
+"""GPU parity of the elementwise / reduction kernels (csrc/elementwise.cu, stem.cu, head.cu) against plain PyTorch
+fp32 (CPU, autograd) on the same bf16-rounded inputs. Outputs are bf16: |err| <= 2^-8 relative per element plus
+fp32 summation-order noise; reductions (fp32) to 1e-4 relative."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc(t, dev):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev)
+
+
+def nchw(t):
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def close_bf16(a, b, extra=0.0):
+    tol = 2 ** -7 * b.abs() + 1e-2 * b.abs().max() * 2 ** -7 + extra
+    assert ((a - b).abs() <= tol).all(), ((a - b).abs().max().item(), b.abs().max().item())
+
+
+@pytest.mark.parametrize("C,H,W,N", [(128, 16, 16, 2), (64, 32, 32, 1), (128, 6, 10, 3)])
+def test_bn_forward_and_residual_tail(cuda_device, C, H, W, N):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    y = bf(torch.randn(N, C, H, W, generator=g) * 2 + 0.5)
+    ys = bf(torch.randn(N, C, H, W, generator=g))
+    x = bf(torch.randn(N, C, H, W, generator=g))
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    d = cuda_device
+    for training in (True, False):
+        stats = torch.stack([y.sum((0, 2, 3)), (y * y).sum((0, 2, 3))]).to(d)
+        rmd, rvd, nbt = rm.clone().to(d), rv.clone().to(d), torch.zeros((), dtype=torch.int64, device=d)
+        bnp = ops.bn_finalize(stats, N * H * W, gamma.to(d), beta.to(d), rmd, rvd, nbt, training=training)
+        rm2, rv2 = rm.clone(), rv.clone()
+        ref = F.batch_norm(y, rm2, rv2, gamma, beta, training=training, momentum=0.1, eps=1e-5)
+        z = nchw(ops.bn_act(nhwc(y, d), bnp, relu=True))
+        close_bf16(z, F.relu(ref))
+        if training:
+            assert torch.allclose(rmd.cpu(), rm2, rtol=1e-4, atol=1e-5) and torch.allclose(rvd.cpu(), rv2, rtol=1e-4)
+            assert int(nbt.item()) == 1
+        else:
+            assert torch.equal(rmd.cpu(), rm) and int(nbt.item()) == 0
+        out = nchw(ops.bn_add_relu(nhwc(y, d), bnp, nhwc(x, d)))
+        close_bf16(out, F.relu(ref + x))
+        stats_s = torch.stack([ys.sum((0, 2, 3)), (ys * ys).sum((0, 2, 3))]).to(d)
+        bnp_s = ops.bn_finalize(stats_s, N * H * W, gamma.to(d), beta.to(d), rm.clone().to(d), rv.clone().to(d),
+                                None, training=training)
+        ref_s = F.batch_norm(ys, rm.clone(), rv.clone(), gamma, beta, training=training, eps=1e-5)
+        out = nchw(ops.bn_add_relu(nhwc(y, d), bnp, nhwc(ys, d), bnp_s))
+        close_bf16(out, F.relu(ref + ref_s))
+
+
+def test_pool_upsample_add(cuda_device):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    d = cuda_device
+    x = bf(torch.randn(2, 128, 12, 20, generator=g))
+    low = bf(torch.randn(2, 128, 6, 10, generator=g))
+    assert torch.equal(nchw(ops.maxpool2(nhwc(x, d))), F.max_pool2d(x, 2, 2))
+    close_bf16(nchw(ops.upsample2_add(nhwc(x, d), nhwc(low, d))), x + F.interpolate(low, scale_factor=2))
+    a, b, c = (bf(torch.randn(2, 128, 4, 4, generator=g)) for _ in range(3))
+    close_bf16(nchw(ops.add(nhwc(a, d), nhwc(b, d), nhwc(c, d))), a + b + c)
+    assert torch.allclose(ops.colsum(nhwc(x, d)).cpu(), x.sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("skip_bn", [False, True])
+def test_bn_backward(cuda_device, skip_bn):
+    """d/dy and d/dys of out = relu(bn(y) + (bn_s(ys) | x)), plus dgamma/dbeta, vs autograd."""
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    d = cuda_device
+    N, C, H, W = 2, 128, 8, 12
+    y = bf(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
+    ys = bf(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, generator=g).requires_grad_(True)
+    gamma_s = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta_s = torch.randn(C, generator=g).requires_grad_(True)
+    dout = bf(torch.randn(N, C, H, W, generator=g))
+    branch = F.batch_norm(ys, None, None, gamma_s, beta_s, training=True) if skip_bn else ys
+    out = F.relu(F.batch_norm(y, None, None, gamma, beta, training=True) + branch)
+    out.backward(dout)
+
+    def stats(t):
+        return torch.stack([t.sum((0, 2, 3)), (t * t).sum((0, 2, 3))]).to(d)
+    bnp = ops.bn_finalize(stats(y.detach()), N * H * W, gamma.detach().to(d), beta.detach().to(d))
+    bnp_s = ops.bn_finalize(stats(ys.detach()), N * H * W, gamma_s.detach().to(d), beta_s.detach().to(d))
+    out_d = nhwc(bf(out.detach()), d)
+    dy, dys, gout, (dg, db), (dgs, dbs) = ops.bn_bwd(
+        nhwc(dout, d), out_d, nhwc(y.detach(), d), bnp, gamma.detach().to(d),
+        ys=nhwc(ys.detach(), d) if skip_bn else None, bnp_s=bnp_s if skip_bn else None,
+        gamma_s=gamma_s.detach().to(d) if skip_bn else None, want_g=True)
+    scale = y.grad.abs().max().item()
+    close_bf16(nchw(dy), y.grad, extra=2e-3 * scale)
+    assert torch.allclose(dg.cpu(), gamma.grad, rtol=2e-3, atol=2e-3 * gamma.grad.abs().max().item())
+    assert torch.allclose(db.cpu(), beta.grad, rtol=2e-3, atol=2e-3 * beta.grad.abs().max().item())
+    gref = dout * (out.detach() > 0)
+    close_bf16(nchw(gout), gref)
+    if skip_bn:
+        close_bf16(nchw(dys), ys.grad, extra=2e-3 * scale)
+        assert torch.allclose(dgs.cpu(), gamma_s.grad, rtol=2e-3, atol=2e-3 * gamma_s.grad.abs().max().item())
+    else:
+        close_bf16(nchw(gout), ys.grad)
+
+
+def test_pool_upsample_backward(cuda_device):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    d = cuda_device
+    x = bf(torch.randn(2, 128, 8, 8, generator=g))
+    x[:, :, :2, :2] = 0.0                                 # ties: the first element of the window gets the gradient
+    x = x.requires_grad_(True)
+    dp = bf(torch.randn(2, 128, 4, 4, generator=g))
+    a1 = bf(torch.randn(2, 128, 8, 8, generator=g))
+    F.max_pool2d(x, 2, 2).backward(dp)
+    dx = nchw(ops.maxpool2_bwd(nhwc(x.detach(), d), nhwc(dp, d), nhwc(a1, d)))
+    close_bf16(dx, x.grad + a1)
+    dx0 = nchw(ops.maxpool2_bwd(nhwc(x.detach(), d), nhwc(dp, d)))
+    assert torch.equal(dx0, x.grad)
+    dout = bf(torch.randn(2, 128, 8, 8, generator=g))
+    low = torch.zeros(2, 128, 4, 4, requires_grad=True)
+    F.interpolate(low, scale_factor=2).backward(dout)
+    close_bf16(nchw(ops.sum2x2(nhwc(dout, d))), low.grad)
+
+
+def test_stem_forward_wgrad(cuda_device):
+    """7x7 stride-2 stem (hourglass.py:163) = im2col (K=147->192) + 1x1 tcgen05 GEMM; wgrad via the 1x1 wgrad kernel."""
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    d = cuda_device
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    w = bf(torch.randn(64, 3, 7, 7, generator=g) * 0.1)
+    b = torch.randn(64, generator=g)
+    ref = F.conv2d(bf(x), w, b, stride=2, padding=3)
+    patches = ops.stem_im2col(x.to(d))
+    stats = torch.zeros(2, 64, device=d)
+    y = ops.conv2d_igemm(patches, ops.stem_pack_weight(w.to(d)), 64, 1, bias=b.to(d), stats=stats)
+    close_bf16(nchw(y), ref, extra=1e-3 * ref.abs().max().item())
+    assert torch.allclose(stats[0].cpu(), ref.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+    dy = bf(torch.randn(2, 64, 32, 48, generator=g))
+    gref = torch.nn.grad.conv2d_weight(bf(x), (64, 3, 7, 7), dy, stride=2, padding=3)
+    gw = ops.conv2d_wgrad(patches, nhwc(dy, d), 147, 1, stem_perm=True).cpu()
+    assert gw.shape == (64, 3, 7, 7)
+    assert ((gw - gref).norm() / gref.norm()).item() <= 1e-4
+
+
+def test_head_backward(cuda_device):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    d = cuda_device
+    feat = bf(torch.randn(2, 128, 16, 16, generator=g)).requires_grad_(True)
+    w = bf(torch.randn(6, 128, 1, 1, generator=g) * 0.1).requires_grad_(True)
+    b = torch.zeros(6, requires_grad=True)
+    dlog_full = torch.randn(2, 2, 6, 16, 16, generator=g)
+    extra = bf(torch.randn(2, 6, 16, 16, generator=g))
+    F.conv2d(feat, w, b).backward(dlog_full[:, 1] + extra)
+    extra_d = ops.to_nhwc(extra.to(d), c_pad=64)
+    dfeat, dw, db = ops.head_backward(dlog_full.to(d)[:, 1], nhwc(feat.detach(), d), ops.pack_weight(w.detach().to(d)),
+                                      6, extra=extra_d)
+    close_bf16(nchw(dfeat), feat.grad, extra=1e-3 * feat.grad.abs().max().item())
+    assert torch.allclose(dw.cpu(), w.grad.view(6, 128), rtol=1e-3, atol=1e-3 * w.grad.abs().max().item())
+    assert torch.allclose(db.cpu(), b.grad, rtol=1e-3, atol=1e-3)

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: images/sec @512x512, train fwd+bwd (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One JSON line on stdout (rank 0). Workload at N=1: BASELINE.json configs[1] — 1-stack hourglass, 2 classes, 512x512,
+batch 32 per GPU, bf16 activations, forward + fused loss + backward (+ one flat NCCL gradient all-reduce for N>1).
+`value`   : device-resident synthetic inputs, CUDA-event timed, max over ranks (weak scaling: 32 images per GPU).
+`e2e`     : the same step through the public API `real_time_helmet_detection_b200.train.train_step` with PINNED HOST
+            inputs: H2D copy of image + targets and a D2H read of the loss inside the timed region, every step.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv 3x3 128->128 @128x128, B=32), timed live here with CUDA
+            events on its launch stream; achieved = algorithmic FLOPs / launch duration vs the measured bf16 peak.
+`cpu_baseline`: the oracle port of the reference path (oracle/, fp32 PyTorch CPU) on the host cores, bounded sample.
+Timing hygiene: >= 3 warm-up steps; the per-step working set (~10 GB of activations) is far larger than the 126 MB
+L2, so no explicit L2 flush is needed between timed iterations (stated in config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMG_TRAIN = {1: 239.189e9, 2: 329.421e9}     # conv FLOPs per 512^2 image, fwd + bwd
+METRIC = "images/sec @512x512 (train fwd+bwd)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 <= ts <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(torch, B, size, seed):
+    from real_time_helmet_detection_b200.synthetic import synthetic_targets
+    g = torch.Generator().manual_seed(777 + seed)
+    image = torch.randn(B, 3, size, size, generator=g)
+    gts = [torch.from_numpy(a) for a in synthetic_targets(B, imsize=size)]
+    return image, gts
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(torch, sd, x, gts, S):
+    """The reference's train-loop body (train.py:99-134) on the oracle port: forward, per-stack loss, backward."""
+    from oracle import hourglass_ref, loss_ref
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    out = hourglass_ref.stacked_hourglass_forward(sd, x, training=True)
+    tot = sum(loss_ref.losses_from_logits(out[:, s], *gts)[3] for s in range(S))
+    tot.backward()
+    return float(tot)
+
+
+def cpu_model(torch, S):
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    torch.manual_seed(777)
+    net = StackedHourglass(S, 128, 6)
+    return {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+            for k, v in net.state_dict().items()}
+
+
+def time_cpu(torch, S, size, batch, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = cpu_model(torch, S)
+    x, gts = synthetic_batch(torch, batch, size, 0)
+    for _ in range(warmup):
+        cpu_reference_step(torch, sd, x, gts, S)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(torch, sd, x, gts, S)
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt, cores
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, size, batch = args.num_stack, args.imsize, 2
+    steps, warmup = max(1, min(args.steps, 30)), max(1, min(args.warmup, 3))
+    ips, dt, cores = time_cpu(torch, S, size, batch, steps, warmup)
+    cpu_name = ""
+    try:
+        cpu_name = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    sample = (f"oracle port of the reference path (fp32 PyTorch CPU), {steps} timed steps of a bounded batch-{batch} "
+              f"sample of the 512x512 workload (fwd + loss + bwd), {cores} threads, {cpu_name}")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{S}-stack hourglass, 2 classes, {size}x{size}, train fwd+bwd", "batch_per_step": batch},
+            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def dominant_kernel_roofline(torch, dev, peaks, reps=20):
+    """conv 3x3 128->128 @128x128, B=32 (8 forward + 8 dgrad instances per step): live CUDA-event timing."""
+    from real_time_helmet_detection_b200 import ops
+    B, H, W, C = 32, 128, 128, 128
+    xs = [torch.randn(B, H, W, C, device=dev).to(torch.bfloat16) for _ in range(3)]   # 3 x 134 MB > L2
+    w = ops.pack_weight(torch.randn(C, C, 3, 3, device=dev) * 0.03)
+    out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+    stats = torch.zeros(2, C, device=dev)
+    for i in range(3):
+        ops.conv2d_igemm(xs[i % 3], w, C, 3, stats=stats, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        ops.conv2d_igemm(xs[i % 3], w, C, 3, stats=stats, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3 / reps
+    flops = 2.0 * B * H * W * C * C * 9
+    achieved = flops / dt / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"bound": "tensor", "kernel": "conv_igemm_kernel<128> 3x3 128->128 @128x128 B=32 (fwd, BN-stat epilogue)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)", "us_per_launch": dt * 1e6,
+            "flops_per_launch": flops, "traffic": None}
+
+
+def decode_latency(torch, dev, S=1, runs=300):
+    """Config 5: decode + NMS at batch 1 (topk 100, conf 0.2, nms 0.2) on the synthetic blob head tensor."""
+    from real_time_helmet_detection_b200.synthetic import synthetic_head
+    from real_time_helmet_detection_b200.evaluate import Prediction
+    head = torch.from_numpy(synthetic_head(S=S)).to(dev)
+    pred = Prediction(None, topk=100, scale_factor=4, conf_th=0.2, nms="nms", nms_th=0.2)
+    for _ in range(10):
+        b, _, _ = pred.decode(head)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(runs)]
+    wall = []
+    for e0, e1 in ev:
+        t0 = time.perf_counter()
+        e0.record()
+        b, c, s = pred.decode(head)       # includes the count D2H read (the one sync the API shape needs)
+        e1.record()
+        wall.append(time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    dev_us = statistics.median(e0.elapsed_time(e1) for e0, e1 in ev) * 1e3
+    return {"workload": f"decode+NMS 512x512 batch 1, {S} stack, topk 100, conf 0.2, nms 0.2", "device_us": dev_us,
+            "host_wall_us": statistics.median(wall) * 1e6, "boxes": int(b[0].shape[0])}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from real_time_helmet_detection_b200 import _lib
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.loss import LossCalculator
+    from real_time_helmet_detection_b200.parallel import attach_flat_allreduce, broadcast_parameters
+    from real_time_helmet_detection_b200.train import train_step
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, size, B = args.num_stack, args.imsize, args.batch
+    peaks = load_peaks()
+
+    torch.manual_seed(777)
+    net = StackedHourglass(S, 128, 6).to(dev).train()
+    crit = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0).to(dev)
+    hook = None
+    if world > 1:
+        broadcast_parameters(net)
+        hook = attach_flat_allreduce(net)
+    image_h, gts_h = synthetic_batch(torch, B, size, rank)
+    image_d, gts_d = image_h.to(dev), [g.to(dev) for g in gts_h]
+    image_p, gts_p = image_h.pin_memory(), [g.pin_memory() for g in gts_h]
+
+    def step_device():
+        for p in net.parameters():
+            p.grad = None
+        return train_step(net, crit, image_d, *gts_d)
+
+    def step_e2e():
+        for p in net.parameters():
+            p.grad = None
+        return float(train_step(net, crit, image_p, *gts_p))     # float(): D2H read of the loss every step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = _lib.lib().hd_launch_count()
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.lib().hd_launch_count() - l0, t0, t1
+
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms, launches, t0, t1 = timed(step_device, args.steps)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    crit.log = {k: [] for k in ("hm", "offset", "size", "total")}
+
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = image_h.numel() * 4 + sum(g.numel() * 4 for g in gts_h)
+
+    if rank == 0:
+        roof = dominant_kernel_roofline(torch, dev, peaks)
+        per_gpu = value / world
+        step_frac = per_gpu * FLOPS_PER_IMG_TRAIN.get(S, 0.0) / (peaks["bf16_tflops_sustained"] * 1e12)
+        roof["step_frac_of_conv_roofline"] = step_frac
+        roof["step_peak"] = f"{peaks['bf16_tflops_sustained']} TFLOP/s sustained ({peaks['source']})"
+        dec = decode_latency(torch, dev, S=1)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ips, dt, cores = time_cpu(torch, S, size, 2, 4, 1)
+            cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+                   "sample": "oracle port (fp32 PyTorch CPU restatement of the reference path), 4 timed steps of a "
+                             f"batch-2 sample of the 512x512 train fwd+loss+bwd workload, {cores} threads"}
+        line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{S}-stack hourglass, 2 classes, {size}x{size}, batch {B}/GPU, bf16, "
+                                       "train fwd + fused focal/L1 loss + bwd" + (", flat NCCL grad all-reduce" if world > 1 else ""),
+                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "no explicit flush: ~10 GB of activations per step >> 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "decode": dec}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if hook is not None:
+            line["allreduce"] = {"calls_per_step": hook.calls / max(1, (warmup + 2 * args.steps + 2)),
+                                 "bytes": hook.elements * 4}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-stack", type=int, default=1)
+    ap.add_argument("--imsize", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

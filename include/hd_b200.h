@@ -28,6 +28,8 @@ typedef struct CUstream_st* hd_stream_t; /* == cudaStream_t */
 
 const char* hd_last_error(void);
 int hd_version(void);
+/* Kernels launched by this library in this process so far (instrumentation for bench.py's gpu_launches). */
+long long hd_launch_count(void);
 
 /* ------------------------------------------------------------------ convolutions (hourglass.py:94-108) */
 

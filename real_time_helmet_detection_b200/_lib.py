@@ -24,6 +24,7 @@ LL = c_longlong
 _SIGNATURES = {
     "hd_last_error": (c_char_p, []),
     "hd_version": (I, []),
+    "hd_launch_count": (LL, []),
     "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_wgrad_ksplit": (I, [I, I, I, I]),

@@ -308,7 +308,7 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     conv_igemm_kernel<BLOCK_N><<<grid, kThreads, smem_bytes, stream>>>(tx, tw, p);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 

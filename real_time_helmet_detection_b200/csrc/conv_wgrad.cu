@@ -204,7 +204,7 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
         attr_set = true;
     }
     conv_wgrad_kernel<BLOCK_N><<<p.groups * p.ksplit, kWgThreads, smem_bytes, stream>>>(tdy, tx, p);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -277,6 +277,6 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     const int total = p.taps * cout * cin_real;
     wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128,
                                                                  cin, accumulate, stem_perm);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

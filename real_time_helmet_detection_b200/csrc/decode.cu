@@ -401,6 +401,6 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
         attr_set = true;
     }
     decode_nms_kernel<<<B, kDecThreads, kDecSmem, stream>>>(a);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

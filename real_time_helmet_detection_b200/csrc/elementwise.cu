@@ -425,7 +425,7 @@ extern "C" int hd_bn_finalize(const float* sum, const float* sqsum, float count,
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
                                                           num_batches_tracked, momentum, eps, training, scale, shift,
                                                           save_mean, save_rstd, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -438,7 +438,7 @@ extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z,
         bn_act_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
     else
         bn_act_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -452,7 +452,7 @@ extern "C" int hd_bn_add_relu(cvp y2, const float* s2, const float* b2, cvp skip
         bn_add_relu_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
     else
         bn_add_relu_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -461,7 +461,7 @@ extern "C" int hd_maxpool2(cvp x, void* y, int N, int H, int W, int C, cudaStrea
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
     maxpool2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BFW(y), N, H, W, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -470,7 +470,7 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     const size_t nvec = static_cast<size_t>(N) * H * W * (C / 8);
     if (nvec == 0) return HD_OK;
     upsample_add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(up1), BF(low), BFW(out), N, H, W, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -493,7 +493,7 @@ extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, cvp y, const float* mean, con
         bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, nullptr,
                                                                  nullptr, nullptr, sums, static_cast<size_t>(npix), C);
     }
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -503,7 +503,7 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
     HD_REQUIRE(C > 0 && C <= 256, "bn_bwd_finalize: C=%d", C);
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(s0, s1, count, gamma, mean, rstd, coef, dgamma, dbeta,
                                                               accumulate, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -521,7 +521,7 @@ extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, cvp y, const float* coef, void
         bn_bwd_apply_kernel<false, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C);
     else
         bn_bwd_apply_kernel<false, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -531,7 +531,7 @@ extern "C" int hd_maxpool2_bwd(cvp x, cvp dpool, cvp add1, cvp add2, void* dx, i
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
     maxpool2_bwd_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -540,7 +540,7 @@ extern "C" int hd_sum2x2(cvp dout, void* dlow, int N, int H, int W, int C, cudaS
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
     sum2x2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(dout), BFW(dlow), N, H, W, C);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -549,7 +549,7 @@ extern "C" int hd_add(cvp a, cvp b, cvp c, void* out, long long nelem, cudaStrea
     const size_t nvec = static_cast<size_t>(nelem) / 8;
     if (nvec == 0) return HD_OK;
     add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(a), BF(b), BF(c), BFW(out), nvec);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -559,6 +559,6 @@ extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaS
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
     colsum_kernel<<<blocks, 256, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(BF(x), out, static_cast<size_t>(npix), C, cs);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

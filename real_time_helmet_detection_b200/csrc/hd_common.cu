@@ -1,6 +1,7 @@
 #include "hd_common.h"
 
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 namespace hd {
@@ -60,6 +61,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return HD_OK;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -77,3 +82,7 @@ int sm_count() {
 extern "C" const char* hd_last_error(void) { return hd::err_buf(); }
 
 extern "C" int hd_version(void) { return 1; }
+
+namespace hd { long long launches(); }
+// Number of kernels this library has launched in this process (bench.py reports it as gpu_launches).
+extern "C" long long hd_launch_count(void) { return hd::launches(); }

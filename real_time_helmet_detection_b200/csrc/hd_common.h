@@ -37,6 +37,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
+void count_launch();   // bumps the kernel-launch counter read by hd_launch_count()
 
 static inline int ilog2_ceil(int v) {
     int l = 0;

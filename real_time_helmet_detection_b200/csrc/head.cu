@@ -113,6 +113,6 @@ extern "C" int hd_head_backward(const float* dlogits, long long bs, const void* 
         dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
         reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
         reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -191,9 +191,9 @@ extern "C" int hd_loss_forward(const float* hm, long long hm_bs, const float* of
     if (rc) return rc;
     HD_CHECK_CUDA(cudaMemsetAsync(sums, 0, 5 * sizeof(float), stream));
     loss_fwd_kernel<<<loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream>>>(a, sums);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     loss_finalize_kernel<<<1, 1, 0, stream>>>(sums, out, static_cast<float>(B), w_hm, w_off, w_size);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -213,6 +213,6 @@ extern "C" int hd_loss_backward(const float* hm, long long hm_bs, const float* o
     g.d_size_bs = d_size_bs; g.fwd_out = fwd_out; g.grad_out = grad_out;
     g.w_hm = w_hm; g.w_off = w_off; g.w_size = w_size;
     loss_bwd_kernel<<<loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream>>>(a, g);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

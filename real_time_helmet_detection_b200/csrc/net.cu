@@ -1,0 +1,573 @@
+// Whole-network executor: StackedHourglass.forward (hourglass.py:223-237) and its autograd as one native,
+// statically planned sequence of kernel launches over a caller-provided HBM arena.
+//
+// The module tree of the reference is walked in C++ (PreLayer :159-173, Hourglass :130-156 recursively,
+// Neck :176-186, Head :189-195, merge convs :215-218/:235); every `Convolution` is one "unit" whose parameter,
+// buffer and gradient pointers arrive in an `hd_unit_ptrs` table filled by the Python nn.Module
+// (real_time_helmet_detection_b200/hourglass.py keeps the reference's state_dict layout). Unit order:
+//   pre.0 | pre.1.{conv1,conv2,skip} | pre.3.{conv1,conv2} | pre.4.{conv1,conv2} |
+//   per stack i: hourglass (26 units, construction order) | neck.1 | neck.2.{conv1,conv2} | head |
+//                [merge_feature.i, merge_prediction.i]  (i < S-1)
+//
+// HBM layout of the arena: [persistent: packed bf16 weights, BN statistics / scale-shift, wgrad split-K scratch]
+// [forward region: every activation the backward pass needs, bump-allocated in execution order]
+// [backward region: gradient temporaries, stack-allocated per block and released on return].
+// All launches go to one stream; nothing synchronises with the host.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "hd_b200.h"
+#include "hd_common.h"
+
+namespace hd {
+
+typedef __nv_bfloat16 bf16;
+
+struct Unit {
+    int cin, cout, k;
+    bool bias, bn;
+    int kind;  // 0 regular, 1 stem (7x7 s2), 2 head, 3 merge_prediction (cin = out_ch)
+    // persistent device buffers
+    bf16* wp = nullptr;    // forward operand
+    bf16* wpd = nullptr;   // dgrad operand
+    float* stats = nullptr;  // [2][cout]
+    float* bnp = nullptr;    // [4][cout] scale, shift, mean, rstd
+    // geometry of the last forward
+    long long npix = 0;
+};
+
+struct ResSaved {
+    int u1, u2, us;  // unit ids (us = -1: identity skip)
+    bf16 *X, *Y1, *Z1, *Y2, *Ys, *Out;
+    int H, W, cin, cout;
+};
+
+struct HgSaved {
+    int up1, low1, low3;   // residual ids
+    int low2_res, low2_hg; // one of them >= 0
+    bf16 *x, *out;
+    int H, W;
+};
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    void* alloc(size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        if (off > peak) peak = off;
+        return p;
+    }
+    bool ok() const { return base == nullptr || peak <= cap; }
+};
+
+}  // namespace hd
+
+using namespace hd;
+
+struct hd_net {
+    int S, in_ch, out_ch;
+    std::vector<Unit> units;
+    std::vector<ResSaved> res;
+    std::vector<HgSaved> hgs;
+    // plan state (valid after a forward)
+    int B = 0, H = 0, W = 0;
+    bool trained_fwd = false;
+    Arena persist, fw, bw;
+    size_t persist_bytes = 0;
+    bool dry = false;
+    int rc = 0;
+    cudaStream_t stream = nullptr;
+    const hd_unit_ptrs* up = nullptr;
+    // saved top-level tensors
+    bf16 *patches = nullptr, *Y0 = nullptr, *Z0 = nullptr, *R1pool = nullptr;
+    int r_pre1 = -1, r_pre3 = -1, r_pre4 = -1;
+    struct StackSaved {
+        int hg_root, neck_res;
+        int u_neck, u_head, u_mf, u_mp;
+        bf16 *x_in, *hg_out, *Yn, *F1, *F2, *pred64, *T;
+    };
+    std::vector<StackSaved> stacks;
+    void* wgrad_ws = nullptr;
+    size_t wgrad_ws_bytes = 0;
+    float* small = nullptr;   // scratch for BN-backward sums / coefficients
+};
+
+static const hd_unit_ptrs kNullUnit{};
+static inline const hd_unit_ptrs& UP(const hd_net* n, int ui) { return n->up ? n->up[ui] : kNullUnit; }
+
+#define RUN(expr)                                   \
+    do {                                            \
+        if (!n->dry && n->rc == 0) n->rc = (expr);  \
+    } while (0)
+
+static inline size_t act_bytes(int B, int H, int W, int C) { return static_cast<size_t>(B) * H * W * C * sizeof(bf16); }
+
+// ------------------------------------------------------------------------------------------------ construction
+static int add_unit(hd_net* n, int cin, int cout, int k, bool bias, bool bn, int kind = 0) {
+    Unit u;
+    u.cin = cin; u.cout = cout; u.k = k; u.bias = bias; u.bn = bn; u.kind = kind;
+    n->units.push_back(u);
+    return static_cast<int>(n->units.size()) - 1;
+}
+
+static int add_residual(hd_net* n, int cin, int cout) {
+    ResSaved r{};
+    r.u1 = add_unit(n, cin, cout, 3, false, true);
+    r.u2 = add_unit(n, cout, cout, 3, false, true);
+    r.us = cin != cout ? add_unit(n, cin, cout, 1, false, true) : -1;
+    r.cin = cin; r.cout = cout;
+    n->res.push_back(r);
+    return static_cast<int>(n->res.size()) - 1;
+}
+
+static int add_hourglass(hd_net* n, int depth, int ch) {
+    HgSaved h{};
+    h.up1 = add_residual(n, ch, ch);
+    h.low1 = add_residual(n, ch, ch);
+    h.low2_res = h.low2_hg = -1;
+    if (depth > 1) h.low2_hg = add_hourglass(n, depth - 1, ch);
+    else h.low2_res = add_residual(n, ch, ch);
+    h.low3 = add_residual(n, ch, ch);
+    n->hgs.push_back(h);
+    return static_cast<int>(n->hgs.size()) - 1;
+}
+
+extern "C" int hd_net_create(int num_stack, int in_ch, int out_ch, hd_net** out) {
+    HD_REQUIRE(num_stack >= 1 && num_stack <= 8, "net_create: num_stack=%d", num_stack);
+    HD_REQUIRE(in_ch == 128, "net_create: hourglass_inch=%d (the sm_100a kernels are specialised for 128 channels)", in_ch);
+    HD_REQUIRE(out_ch >= 5 && out_ch <= 16, "net_create: out_ch=%d (num_cls+4 must be in [5,16])", out_ch);
+    hd_net* n = new (std::nothrow) hd_net();
+    HD_REQUIRE(n != nullptr, "net_create: out of host memory");
+    n->S = num_stack; n->in_ch = in_ch; n->out_ch = out_ch;
+    add_unit(n, 3, 64, 7, true, true, 1);
+    n->r_pre1 = add_residual(n, 64, 128);
+    n->r_pre3 = add_residual(n, 128, 128);
+    n->r_pre4 = add_residual(n, 128, in_ch);
+    for (int i = 0; i < num_stack; ++i) {
+        hd_net::StackSaved s{};
+        s.hg_root = add_hourglass(n, 4, in_ch);
+        s.u_neck = add_unit(n, in_ch, in_ch, 1, true, true);
+        s.neck_res = add_residual(n, in_ch, in_ch);
+        s.u_head = add_unit(n, in_ch, out_ch, 1, true, false, 2);
+        s.u_mf = s.u_mp = -1;
+        if (i < num_stack - 1) {
+            s.u_mf = add_unit(n, in_ch, in_ch, 1, true, false);
+            s.u_mp = add_unit(n, out_ch, in_ch, 1, true, false, 3);
+        }
+        n->stacks.push_back(s);
+    }
+    *out = n;
+    return HD_OK;
+}
+
+extern "C" void hd_net_destroy(hd_net* n) { delete n; }
+extern "C" int hd_net_num_units(const hd_net* n) { return static_cast<int>(n->units.size()); }
+
+// ------------------------------------------------------------------------------------------------ helpers
+static inline int block_n_for(int cout) { return cout > 64 ? 128 : (cout > 16 ? 64 : 16); }
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+static void plan_persistent(hd_net* n) {
+    Arena& a = n->persist;
+    size_t stats_total = 0;
+    for (Unit& u : n->units) stats_total += 2 * static_cast<size_t>(u.cout);
+    float* stats = reinterpret_cast<float*>(a.alloc(stats_total * sizeof(float)));
+    size_t so = 0;
+    for (Unit& u : n->units) {
+        u.stats = stats ? stats + so : nullptr;
+        so += 2 * u.cout;
+        u.bnp = reinterpret_cast<float*>(a.alloc(4 * u.cout * sizeof(float)));
+        const int taps = u.kind == 1 ? 1 : u.k * u.k;
+        if (u.kind == 1) {
+            u.wp = reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(64) * 192 * 2));
+            u.wpd = nullptr;
+        } else {
+            u.wp = reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(taps) * block_n_for(u.cout) * pad64(u.cin) * 2));
+            u.wpd = u.kind == 2 ? nullptr
+                                : reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(taps) * block_n_for(u.cin) *
+                                                                  pad64(u.cout) * 2));
+        }
+    }
+    n->small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
+    n->persist_bytes = stats_total * sizeof(float);
+}
+
+static void pack_weights(hd_net* n, bool need_dgrad) {
+    for (size_t i = 0; i < n->units.size(); ++i) {
+        Unit& u = n->units[i];
+        const hd_unit_ptrs& p = UP(n, static_cast<int>(i));
+        if (u.kind == 1) {
+            RUN(hd_stem_pack_weight(p.w, u.wp, u.cout, n->stream));
+            continue;
+        }
+        RUN(hd_pack_conv_weight(p.w, u.wp, u.cout, u.cin, u.k, block_n_for(u.cout), pad64(u.cin), 0, n->stream));
+        if (need_dgrad && u.wpd)
+            RUN(hd_pack_conv_weight(p.w, u.wpd, u.cout, u.cin, u.k, block_n_for(u.cin), pad64(u.cout), 1, n->stream));
+    }
+}
+
+// conv (+ bias) -> raw output + BN statistics; then finalize the BN of this unit
+static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, int W, const bf16* addend, int training) {
+    Unit& u = n->units[ui];
+    const hd_unit_ptrs& p = UP(n, ui);
+    const int cin_gemm = u.kind == 1 ? 192 : pad64(u.cin);
+    const int k = u.kind == 1 ? 1 : u.k;
+    const bool stats = u.bn && training;
+    u.npix = static_cast<long long>(B) * H * W;
+    RUN(hd_conv2d_igemm(x, u.wp, y, nullptr, u.bias ? p.b : nullptr, addend, stats ? u.stats : nullptr,
+                        stats ? u.stats + u.cout : nullptr, B, H, W, cin_gemm, u.cout, block_n_for(u.cout), k, 0,
+                        u.cout, 0, 0, 1, n->stream));
+    if (u.bn)
+        RUN(hd_bn_finalize(u.stats, u.stats + u.cout, static_cast<float>(u.npix), p.gamma, p.beta, p.running_mean,
+                           p.running_var, p.num_batches_tracked, 0.1f, 1e-5f, training, u.bnp, u.bnp + u.cout,
+                           u.bnp + 2 * u.cout, u.bnp + 3 * u.cout, u.cout, n->stream));
+}
+
+static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int training) {
+    ResSaved& r = n->res[ri];
+    r.X = X; r.H = H; r.W = W;
+    const size_t bytes = act_bytes(B, H, W, r.cout);
+    const long long npix = static_cast<long long>(B) * H * W;
+    r.Y1 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    r.Z1 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    r.Y2 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    r.Ys = r.us >= 0 ? reinterpret_cast<bf16*>(n->fw.alloc(bytes)) : nullptr;
+    r.Out = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    Unit &u1 = n->units[r.u1], &u2 = n->units[r.u2];
+    conv_unit(n, r.u1, X, r.Y1, B, H, W, nullptr, training);
+    RUN(hd_bn_act(r.Y1, u1.bnp, u1.bnp + u1.cout, r.Z1, npix, r.cout, 1, n->stream));
+    conv_unit(n, r.u2, r.Z1, r.Y2, B, H, W, nullptr, training);
+    if (r.us >= 0) {
+        Unit& us = n->units[r.us];
+        conv_unit(n, r.us, X, r.Ys, B, H, W, nullptr, training);
+        RUN(hd_bn_add_relu(r.Y2, u2.bnp, u2.bnp + u2.cout, r.Ys, us.bnp, us.bnp + us.cout, r.Out, npix, r.cout,
+                           n->stream));
+    } else {
+        RUN(hd_bn_add_relu(r.Y2, u2.bnp, u2.bnp + u2.cout, X, nullptr, nullptr, r.Out, npix, r.cout, n->stream));
+    }
+    return r.Out;
+}
+
+static bf16* hourglass_fwd(hd_net* n, int hi, bf16* x, int B, int H, int W, int training) {
+    HgSaved& h = n->hgs[hi];
+    h.x = x; h.H = H; h.W = W;
+    const int C = n->in_ch;
+    bf16* up1 = residual_fwd(n, h.up1, x, B, H, W, training);
+    bf16* pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H / 2, W / 2, C)));
+    RUN(hd_maxpool2(x, pool, B, H, W, C, n->stream));
+    bf16* low1 = residual_fwd(n, h.low1, pool, B, H / 2, W / 2, training);
+    bf16* low2 = h.low2_hg >= 0 ? hourglass_fwd(n, h.low2_hg, low1, B, H / 2, W / 2, training)
+                                : residual_fwd(n, h.low2_res, low1, B, H / 2, W / 2, training);
+    bf16* low3 = residual_fwd(n, h.low3, low2, B, H / 2, W / 2, training);
+    h.out = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H, W, C)));
+    RUN(hd_upsample2_add(up1, low3, h.out, B, H, W, C, n->stream));
+    return h.out;
+}
+
+static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H, int W, int training) {
+    const int C = n->in_ch;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+    if (!n->dry) {
+        if (n->rc == 0 && cudaMemsetAsync(n->units[0].stats, 0, n->persist_bytes, n->stream) != cudaSuccess)
+            n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN statistics failed");
+        pack_weights(n, training != 0);
+    }
+    // ---- PreLayer (hourglass.py:159-173)
+    Unit& u0 = n->units[0];
+    n->patches = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 192)));
+    n->Y0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
+    n->Z0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
+    RUN(hd_stem_im2col(x, n->patches, B, H, W, n->stream));
+    conv_unit(n, 0, n->patches, n->Y0, B, H2, W2, nullptr, training);
+    RUN(hd_bn_act(n->Y0, u0.bnp, u0.bnp + 64, n->Z0, static_cast<long long>(B) * H2 * W2, 64, 1, n->stream));
+    bf16* r1 = residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training);
+    n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
+    RUN(hd_maxpool2(r1, n->R1pool, B, H2, W2, 128, n->stream));
+    bf16* r3 = residual_fwd(n, n->r_pre3, n->R1pool, B, H4, W4, training);
+    bf16* xcur = residual_fwd(n, n->r_pre4, r3, B, H4, W4, training);
+    // ---- stacks (hourglass.py:226-235)
+    const long long npix4 = static_cast<long long>(B) * H4 * W4;
+    for (int i = 0; i < n->S; ++i) {
+        hd_net::StackSaved& s = n->stacks[i];
+        s.x_in = xcur;
+        s.hg_out = hourglass_fwd(n, s.hg_root, xcur, B, H4, W4, training);
+        Unit& un = n->units[s.u_neck];
+        s.Yn = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
+        s.F1 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
+        conv_unit(n, s.u_neck, s.hg_out, s.Yn, B, H4, W4, nullptr, training);
+        RUN(hd_bn_act(s.Yn, un.bnp, un.bnp + C, s.F1, npix4, C, 1, n->stream));
+        s.F2 = residual_fwd(n, s.neck_res, s.F1, B, H4, W4, training);
+        Unit& uh = n->units[s.u_head];
+        const bool merge = i < n->S - 1;
+        s.pred64 = merge ? reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 64))) : nullptr;
+        if (merge && !n->dry && n->rc == 0 &&
+            cudaMemsetAsync(s.pred64, 0, act_bytes(B, H4, W4, 64), n->stream) != cudaSuccess)
+            n->rc = fail(HD_ERR_CUDA, "net_forward: memset failed");
+        RUN(hd_conv2d_igemm(s.F2, uh.wp, logits, s.pred64, UP(n, s.u_head).b, nullptr, nullptr, nullptr, B, H4, W4, C,
+                            n->out_ch, 16, 1, 1, 0, 64, i, n->S, n->stream));
+        if (merge) {
+            // x = x + merge_feature(feature) + merge_prediction(prediction)   (hourglass.py:235)
+            s.T = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
+            bf16* xn = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
+            conv_unit(n, s.u_mf, s.F2, s.T, B, H4, W4, xcur, training);
+            conv_unit(n, s.u_mp, s.pred64, xn, B, H4, W4, s.T, training);
+            xcur = xn;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, int H, int W) {
+    Unit& u = n->units[ui];
+    const hd_unit_ptrs& p = UP(n, ui);
+    if (u.kind == 1)
+        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->stream));
+    else
+        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->stream));
+}
+
+static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H, int W, const bf16* addend) {
+    Unit& u = n->units[ui];
+    RUN(hd_conv2d_igemm(dy, u.wpd, dx, nullptr, nullptr, addend, nullptr, nullptr, B, H, W, pad64(u.cout), u.cin,
+                        block_n_for(u.cin), u.k, 0, u.cin, 0, 0, 1, n->stream));
+}
+
+// BN (+ReLU) backward of one unit: g = dout * (out > 0) -> dy (and the skip branch / g when requested)
+static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, const bf16* y, bf16* dy, int us,
+                        const bf16* ys, bf16* dys, bf16* gout) {
+    Unit& u = n->units[ui];
+    const hd_unit_ptrs& p = UP(n, ui);
+    const int C = u.cout;
+    float* sums = n->small;            // [3][C]
+    float* coef = n->small + 3 * 256;  // [3][C]
+    float* coef_s = n->small + 6 * 256;
+    if (!n->dry && n->rc == 0 && cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), n->stream) != cudaSuccess)
+        n->rc = fail(HD_ERR_CUDA, "net_backward: memset failed");
+    const float* mean = u.bnp + 2 * C;
+    const float* rstd = u.bnp + 3 * C;
+    const Unit* s = us >= 0 ? &n->units[us] : nullptr;
+    RUN(hd_bn_bwd_reduce(dout, out, y, mean, rstd, ys, s ? s->bnp + 2 * C : nullptr, s ? s->bnp + 3 * C : nullptr, sums,
+                         u.npix, C, n->stream));
+    RUN(hd_bn_bwd_finalize(sums, sums + C, static_cast<float>(u.npix), p.gamma, mean, rstd, coef, p.dgamma, p.dbeta, 0,
+                           C, n->stream));
+    if (s) {
+        const hd_unit_ptrs& ps = UP(n, us);
+        RUN(hd_bn_bwd_finalize(sums, sums + 2 * C, static_cast<float>(u.npix), ps.gamma, s->bnp + 2 * C,
+                               s->bnp + 3 * C, coef_s, ps.dgamma, ps.dbeta, 0, C, n->stream));
+    }
+    RUN(hd_bn_bwd_apply(dout, out, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout, u.npix, C, n->stream));
+}
+
+static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
+    ResSaved& r = n->res[ri];
+    const int H = r.H, W = r.W;
+    const size_t mark = n->bw.off;
+    const size_t bytes_o = act_bytes(B, H, W, r.cout), bytes_i = act_bytes(B, H, W, r.cin);
+    bf16* dY2 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
+    bf16* dYs = r.us >= 0 ? reinterpret_cast<bf16*>(n->bw.alloc(bytes_o)) : nullptr;
+    bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
+    bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G);
+    wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W);
+    bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
+    dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
+    bf16* dY1 = dY2;  // dY2 is dead after its dgrad / wgrad: reuse the buffer
+    bn_bwd_unit(n, r.u1, dZ1, r.Z1, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
+    wgrad_unit(n, r.u1, r.X, dY1, B, H, W);
+    if (r.us < 0) {
+        dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
+    } else {
+        bf16* dXa = reinterpret_cast<bf16*>(n->bw.alloc(bytes_i));
+        dgrad_unit(n, r.u1, dY1, dXa, B, H, W, nullptr);
+        dgrad_unit(n, r.us, dYs, dX, B, H, W, dXa);
+    }
+    if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W);
+    n->bw.off = mark;
+}
+
+static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const bf16* extra_add, int B) {
+    HgSaved& h = n->hgs[hi];
+    const int H = h.H, W = h.W, C = n->in_ch;
+    const size_t mark = n->bw.off;
+    const size_t half = act_bytes(B, H / 2, W / 2, C), full = act_bytes(B, H, W, C);
+    bf16* d_low3 = reinterpret_cast<bf16*>(n->bw.alloc(half));
+    RUN(hd_sum2x2(dOut, d_low3, B, H, W, C, n->stream));
+    bf16* d_low2 = reinterpret_cast<bf16*>(n->bw.alloc(half));
+    residual_bwd(n, h.low3, d_low3, d_low2, B);
+    bf16* d_low1 = d_low3;  // d_low3 is dead
+    if (h.low2_hg >= 0) hourglass_bwd(n, h.low2_hg, d_low2, d_low1, nullptr, B);
+    else residual_bwd(n, h.low2_res, d_low2, d_low1, B);
+    bf16* d_pool = d_low2;  // dead as well
+    residual_bwd(n, h.low1, d_low1, d_pool, B);
+    bf16* d_xa = reinterpret_cast<bf16*>(n->bw.alloc(full));
+    residual_bwd(n, h.up1, dOut, d_xa, B);
+    RUN(hd_maxpool2_bwd(h.x, d_pool, d_xa, extra_add, dX, B, H, W, C, n->stream));
+    n->bw.off = mark;
+}
+
+static void backward_impl(hd_net* n, const float* dlogits) {
+    const int B = n->B, C = n->in_ch;
+    const int H2 = n->H / 2, W2 = n->W / 2, H4 = n->H / 4, W4 = n->W / 4;
+    const size_t full4 = act_bytes(B, H4, W4, C);
+    const long long hw4 = static_cast<long long>(H4) * W4;
+    const long long npix4 = static_cast<long long>(B) * hw4;
+    bf16* dXn = nullptr;  // gradient w.r.t. the input of stack i+1
+    for (int i = n->S - 1; i >= 0; --i) {
+        hd_net::StackSaved& s = n->stacks[i];
+        const bool merge = i < n->S - 1;
+        bf16* dpred = nullptr;
+        bf16* dF2m = nullptr;
+        if (merge) {
+            const hd_unit_ptrs& pmf = UP(n, s.u_mf);
+            const hd_unit_ptrs& pmp = UP(n, s.u_mp);
+            RUN(hd_colsum(dXn, pmp.db, npix4, C, C, n->stream));
+            RUN(hd_colsum(dXn, pmf.db, npix4, C, C, n->stream));
+            wgrad_unit(n, s.u_mp, s.pred64, dXn, B, H4, W4);
+            wgrad_unit(n, s.u_mf, s.F2, dXn, B, H4, W4);
+            dpred = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H4, W4, 16)));
+            Unit& ump = n->units[s.u_mp];
+            RUN(hd_conv2d_igemm(dXn, ump.wpd, dpred, nullptr, nullptr, nullptr, nullptr, nullptr, B, H4, W4, C,
+                                n->out_ch, 16, 1, 0, 16, 0, 0, 1, n->stream));
+        }
+        // head
+        bf16* dF2 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+        const hd_unit_ptrs& ph = UP(n, s.u_head);
+        RUN(hd_head_backward(dlogits + static_cast<long long>(i) * n->out_ch * hw4,
+                             static_cast<long long>(n->S) * n->out_ch * hw4, dpred, 16, s.F2, n->units[s.u_head].wp,
+                             dF2, ph.dw, ph.db, B, H4, W4, n->out_ch, n->stream));
+        if (merge) {
+            dF2m = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+            dgrad_unit(n, s.u_mf, dXn, dF2m, B, H4, W4, dF2);
+            dF2 = dF2m;
+        }
+        // neck: Residual, then conv1x1 + bias + BN + ReLU
+        bf16* dF1 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+        residual_bwd(n, s.neck_res, dF2, dF1, B);
+        bf16* dYn = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+        bn_bwd_unit(n, s.u_neck, dF1, s.F1, s.Yn, dYn, -1, nullptr, nullptr, nullptr);
+        RUN(hd_colsum(dYn, UP(n, s.u_neck).db, npix4, C, C, n->stream));
+        wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4);
+        bf16* dHg = dF1;  // dead
+        dgrad_unit(n, s.u_neck, dYn, dHg, B, H4, W4, nullptr);
+        bf16* dXi = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+        hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);
+        dXn = dXi;
+    }
+    // PreLayer
+    bf16* dR3 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+    residual_bwd(n, n->r_pre4, dXn, dR3, B);
+    bf16* dP = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+    residual_bwd(n, n->r_pre3, dR3, dP, B);
+    bf16* dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
+    RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
+    residual_bwd(n, n->r_pre1, dR1, dZ0, B);
+    bf16* dY0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
+    bn_bwd_unit(n, 0, dZ0, n->Z0, n->Y0, dY0, -1, nullptr, nullptr, nullptr);
+    RUN(hd_colsum(dY0, UP(n, 0).db, static_cast<long long>(B) * H2 * W2, 64, 64, n->stream));
+    wgrad_unit(n, 0, n->patches, dY0, B, H2, W2);
+}
+
+// ------------------------------------------------------------------------------------------------ planning + entry points
+static size_t max_wgrad_ws(int B, int H, int W) {
+    size_t m = 0;
+    const int H2 = H / 2, W2 = W / 2;
+    size_t v = hd_conv2d_wgrad_workspace_bytes(B, H2, W2, 192, 1); if (v > m) m = v;
+    v = hd_conv2d_wgrad_workspace_bytes(B, H2, W2, 128, 3); if (v > m) m = v;
+    for (int h = H / 4, w = W / 4; h >= 1 && w >= 1; h /= 2, w /= 2) {
+        v = hd_conv2d_wgrad_workspace_bytes(B, h, w, 128, 3);
+        if (v > m) m = v;
+    }
+    return m;
+}
+
+static void plan(hd_net* n, uint8_t* base, size_t cap, int B, int H, int W, bool with_backward, size_t* total) {
+    // persistent | wgrad scratch | forward | backward
+    n->persist = Arena(); n->fw = Arena(); n->bw = Arena();
+    n->persist.base = base; n->persist.cap = cap;
+    plan_persistent(n);
+    size_t off = (n->persist.peak + 255) & ~size_t(255);
+    n->wgrad_ws_bytes = with_backward ? max_wgrad_ws(B, H, W) : 0;
+    n->wgrad_ws = base ? base + off : nullptr;
+    off += (n->wgrad_ws_bytes + 255) & ~size_t(255);
+    n->fw.base = base ? base + off : nullptr;
+    n->fw.cap = cap > off ? cap - off : 0;
+    *total = off;
+}
+
+extern "C" size_t hd_net_workspace_bytes(hd_net* n, int B, int H, int W, int with_backward) {
+    if (B <= 0 || H <= 0 || W <= 0 || H % 64 || W % 64) return 0;
+    size_t head = 0;
+    n->dry = true; n->rc = 0; n->up = nullptr;
+    plan(n, nullptr, 0, B, H, W, with_backward != 0, &head);
+    n->B = B; n->H = H; n->W = W;
+    forward_impl(n, nullptr, nullptr, B, H, W, 1);
+    size_t total = head + ((n->fw.peak + 255) & ~size_t(255));
+    if (with_backward) {
+        n->bw = Arena();
+        backward_impl(n, nullptr);
+        total += (n->bw.peak + 255) & ~size_t(255);
+    }
+    n->dry = false;
+    n->trained_fwd = false;
+    return total + 4096;
+}
+
+extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* x, float* logits,
+                              void* workspace, size_t workspace_bytes, int B, int H, int W, int training,
+                              hd_stream_t stream) {
+    HD_REQUIRE(n && units && x && logits && workspace, "net_forward: null argument");
+    HD_REQUIRE(n_units == static_cast<int>(n->units.size()), "net_forward: %d units given, the network has %d", n_units,
+               static_cast<int>(n->units.size()));
+    HD_REQUIRE(B > 0 && H > 0 && W > 0 && H % 64 == 0 && W % 64 == 0,
+               "net_forward: input (%d,3,%d,%d): H and W must be positive multiples of 64", B, H, W);
+    HD_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "net_forward: workspace must be 256-byte aligned");
+    size_t head = 0;
+    n->dry = false; n->rc = 0; n->up = units; n->stream = stream;
+    plan(n, reinterpret_cast<uint8_t*>(workspace), workspace_bytes, B, H, W, training != 0, &head);
+    n->B = B; n->H = H; n->W = W;
+    // capacity check with a dry pass first (cheap: pointer arithmetic only)
+    {
+        n->dry = true;
+        Arena keep = n->fw;
+        forward_impl(n, nullptr, nullptr, B, H, W, training);
+        const size_t need = head + n->fw.peak;
+        n->fw = keep;
+        n->dry = false;
+        HD_REQUIRE(need <= workspace_bytes, "net_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    }
+    forward_impl(n, x, logits, B, H, W, training);
+    n->trained_fwd = training != 0 && n->rc == 0;
+    // backward region starts after the forward region
+    const size_t fw_end = head + ((n->fw.peak + 255) & ~size_t(255));
+    n->bw = Arena();
+    n->bw.base = reinterpret_cast<uint8_t*>(workspace) + fw_end;
+    n->bw.cap = workspace_bytes > fw_end ? workspace_bytes - fw_end : 0;
+    return n->rc;
+}
+
+extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* dlogits,
+                               void* workspace, size_t workspace_bytes, hd_stream_t stream) {
+    HD_REQUIRE(n && units && dlogits && workspace, "net_backward: null argument");
+    HD_REQUIRE(n_units == static_cast<int>(n->units.size()), "net_backward: unit table size mismatch");
+    HD_REQUIRE(n->trained_fwd, "net_backward: no training-mode forward pass is pending on this network");
+    HD_REQUIRE(reinterpret_cast<uint8_t*>(workspace) == n->persist.base, "net_backward: workspace moved since the forward pass");
+    n->up = units; n->stream = stream; n->rc = 0;
+    // capacity check (dry) then run
+    Arena keep = n->bw;
+    n->dry = true;
+    backward_impl(n, nullptr);
+    const size_t need = n->bw.peak;
+    n->bw = keep;
+    n->bw.off = 0; n->bw.peak = 0;
+    n->dry = false;
+    HD_REQUIRE(need <= n->bw.cap, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)",
+               n->bw.cap, need);
+    backward_impl(n, dlogits);
+    n->trained_fwd = false;
+    return n->rc;
+}

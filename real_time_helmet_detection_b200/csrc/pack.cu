@@ -65,7 +65,7 @@ extern "C" int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int
     const int total = ksize * ksize * rows_pad * k_pad;
     pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(out), cout,
                                                                 cin, ksize * ksize, rows_pad, k_pad, mode);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -77,7 +77,7 @@ extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, i
     if (total == 0) return HD_OK;
     nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), N,
                                                                             C, H, W, c_pad);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -89,6 +89,6 @@ extern "C" int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, i
     if (total == 0) return HD_OK;
     nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                                             y, N, C, H, W, c_stride);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

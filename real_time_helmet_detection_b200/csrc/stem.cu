@@ -68,7 +68,7 @@ extern "C" int hd_stem_im2col(const float* x, void* patches, int N, int H, int W
     if (g > cap) g = cap;
     stem_im2col_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), N,
                                                                    H, W);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
 
@@ -77,6 +77,6 @@ extern "C" int hd_stem_pack_weight(const float* w, void* out, int cout, cudaStre
     HD_REQUIRE(cout > 0 && cout <= 64, "stem_pack_weight: cout=%d", cout);
     const int total = cout * kStemKPad;
     stem_pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), cout);
-    HD_CHECK_CUDA(cudaGetLastError());
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

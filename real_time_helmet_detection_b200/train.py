@@ -1,0 +1,49 @@
+"""Training-step driver — the body of the reference's hot loop (train.py:92-139) over the B200 kernels.
+
+`train_step` is the call a user of this package makes per iteration: host (or device) batch in, scalar loss out,
+parameter gradients accumulated. It mirrors train.py:97-136: forward, per-stack split + head activation + loss
+(fused into one kernel per stack here), sum over stacks, optional GradScaler, backward, optional optimizer step.
+`load_network` mirrors train.py:164-201 for the pieces on the hot path (network + loss calculator factory).
+"""
+from __future__ import annotations
+
+import torch
+
+from .hourglass import StackedHourglass
+from .loss import LossCalculator
+
+
+def load_network(args, device):
+    """Same argument names as the reference's argparse namespace (config.py); returns (network, loss_calculator)."""
+    network = StackedHourglass(num_stack=args.num_stack, in_ch=args.hourglass_inch, out_ch=args.num_cls + 4,
+                               increase_ch=args.increase_ch, activation=args.activation, pool=args.pool,
+                               neck_activation=args.neck_activation, neck_pool=args.neck_pool).to(device)
+    loss_calculator = LossCalculator(hm_weight=args.hm_weight, offset_weight=args.offset_weight,
+                                     size_weight=args.size_weight, focal_alpha=args.focal_alpha,
+                                     focal_beta=args.focal_beta).to(device)
+    return network, loss_calculator
+
+
+def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, gt_mask, num_cls=2,
+               normalized_coord=False, scaler=None, optimizer=None):
+    """One iteration of train.py:92-139. Tensors may live on the host (pinned for async copies) or the device."""
+    device = next(network.parameters()).device
+    image = image.to(device, non_blocking=True)
+    gts = [t.to(device, non_blocking=True) for t in (gt_heatmap, gt_offset, gt_size, gt_mask)]   # once, not per stack
+    outputs = network(image)                                   # (B, S, num_cls+4, H/4, W/4) fp32 logits
+    total_loss = 0
+    for s in range(outputs.shape[1]):
+        total_loss = total_loss + loss_calculator.forward_logits(outputs[:, s], *gts, num_cls=num_cls,
+                                                                 normalized_coord=normalized_coord)
+    if scaler is not None:
+        scaler.scale(total_loss).backward()
+        if optimizer is not None:
+            scaler.step(optimizer)
+            scaler.update()
+    else:
+        total_loss.backward()
+        if optimizer is not None:
+            optimizer.step()
+    if optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    return total_loss.detach()

@@ -64,7 +64,7 @@ def gt_for(ref_tf, size, batch):
 
 def golden_hourglass(ref_hg, ref_loss, ref_tf):
     for S in (1, 2):
-        for size in (64, 128):
+        for size in (128, 192):
             torch.manual_seed(777)
             net = ref_hg.StackedHourglass(num_stack=S, in_ch=128, out_ch=6)
             x = torch.randn(2, 3, size, size, generator=torch.Generator().manual_seed(1))

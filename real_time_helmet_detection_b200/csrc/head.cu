@@ -9,47 +9,71 @@
 namespace hd {
 
 constexpr int kHeadMaxC = 16;
+constexpr int kHeadTile = 64;   // pixels per CTA iteration
 
-__global__ void head_bwd_kernel(const float* __restrict__ dlogits, long long bs, int HW, int cout,
-                                const __nv_bfloat16* __restrict__ extra, int extra_cs,
-                                const __nv_bfloat16* __restrict__ feat, const __nv_bfloat16* __restrict__ wp,
-                                __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ dbias,
-                                long long npix) {
-    // 16 lanes per pixel, 8 feature channels each (128 channels); blockDim = 256 -> 16 pixels per pass
-    __shared__ float s_w[kHeadMaxC][128];
-    __shared__ float s_red[16][kHeadMaxC * 8 + 1];
-    for (int i = threadIdx.x; i < cout * 128; i += blockDim.x) s_w[i / 128][i % 128] = __bfloat162float(wp[i]);
-    __syncthreads();
+// 256 threads: 16 lanes (8 feature channels each) x 16 pixel rows; a tile of 64 pixels is handled as 4 pixels per
+// thread (4 independent 16-byte loads in flight). The per-pixel gradient vectors g[c] are staged coalesced in
+// shared memory first. dW partials stay in registers for the CTA's whole pixel range.
+template <int MAXC>
+__global__ void __launch_bounds__(256, MAXC <= 8 ? 2 : 1)
+head_bwd_kernel(const float* __restrict__ dlogits, long long bs, int HW, int cout,
+                const __nv_bfloat16* __restrict__ extra, int extra_cs, const __nv_bfloat16* __restrict__ feat,
+                const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw,
+                float* __restrict__ dbias, long long npix) {
+    __shared__ float s_w[MAXC][128];
+    __shared__ float s_g[MAXC][kHeadTile];
+    __shared__ float s_red[16][MAXC * 8 + 1];
+    for (int i = threadIdx.x; i < MAXC * 128; i += blockDim.x)
+        s_w[i / 128][i % 128] = (i / 128) < cout ? __bfloat162float(wp[i]) : 0.f;
     const int lane_c = threadIdx.x & 15, row = threadIdx.x >> 4;
     const int k0 = lane_c * 8;
-    float acc[kHeadMaxC][8];
-    float accb[kHeadMaxC];
+    float acc[MAXC][8];
+    float accb[MAXC];
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
         accb[c] = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
     }
-    for (long long pix = static_cast<long long>(blockIdx.x) * 16 + row; pix < npix;
-         pix += static_cast<long long>(gridDim.x) * 16) {
-        const long long n = pix / HW, p = pix - n * HW;
-        uint4 u = *reinterpret_cast<const uint4*>(feat + pix * 128 + k0);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 t = __bfloat1622float2(h[j]);
-            f[2 * j] = t.x;
-            f[2 * j + 1] = t.y;
-        }
-        float d[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = 0.f;
-#pragma unroll
-        for (int c = 0; c < kHeadMaxC; ++c) {
-            if (c < cout) {
-                float g = dlogits[n * bs + static_cast<long long>(c) * HW + p];
+    const long long ntiles = (npix + kHeadTile - 1) / kHeadTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p0 = tile * kHeadTile;
+        __syncthreads();
+        for (int i = threadIdx.x; i < MAXC * kHeadTile; i += blockDim.x) {
+            const int c = i / kHeadTile, lp = i - c * kHeadTile;
+            const long long pix = p0 + lp;
+            float g = 0.f;
+            if (c < cout && pix < npix) {
+                const long long n = pix / HW, p = pix - n * HW;
+                g = dlogits[n * bs + static_cast<long long>(c) * HW + p];
                 if (extra) g += __bfloat162float(extra[pix * extra_cs + c]);
+            }
+            s_g[c][lp] = g;
+        }
+        __syncthreads();
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long pix = p0 + row + 16 * q;
+            u[q] = pix < npix ? *reinterpret_cast<const uint4*>(feat + pix * 128 + k0) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int lp = row + 16 * q;
+            const long long pix = p0 + lp;
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[q]);
+            float f[8], d[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 t = __bfloat1622float2(h[j]);
+                f[2 * j] = t.x;
+                f[2 * j + 1] = t.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                const float g = s_g[c][lp];
                 accb[c] += g;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -57,19 +81,21 @@ __global__ void head_bwd_kernel(const float* __restrict__ dlogits, long long bs,
                     acc[c][j] = fmaf(g, f[j], acc[c][j]);
                 }
             }
-        }
-        uint4 o;
-        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            if (pix < npix) {
+                uint4 o;
+                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
-        *reinterpret_cast<uint4*>(dfeat + pix * 128 + k0) = o;
+                for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+                *reinterpret_cast<uint4*>(dfeat + pix * 128 + k0) = o;
+            }
+        }
     }
     // reduce the 16 pixel rows of the block, one channel-vector (lane_c) at a time
     for (int lc = 0; lc < 16; ++lc) {
         __syncthreads();
         if (lane_c == lc) {
 #pragma unroll
-            for (int c = 0; c < kHeadMaxC; ++c)
+            for (int c = 0; c < MAXC; ++c)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s_red[row][c * 8 + j] = acc[c][j];
         }
@@ -84,7 +110,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dlogits, long long bs,
     __syncthreads();
     if (lane_c == 0) {
 #pragma unroll
-        for (int c = 0; c < kHeadMaxC; ++c) s_red[row][c] = accb[c];
+        for (int c = 0; c < MAXC; ++c) s_red[row][c] = accb[c];
     }
     __syncthreads();
     if (threadIdx.x < cout) {
@@ -105,14 +131,25 @@ extern "C" int hd_head_backward(const float* dlogits, long long bs, const void* 
     HD_REQUIRE(cout >= 1 && cout <= kHeadMaxC, "head_backward: cout=%d", cout);
     HD_REQUIRE(N > 0 && H > 0 && W > 0, "head_backward: empty tensor");
     const long long npix = static_cast<long long>(N) * H * W;
-    long long g = (npix + 63) / 64;
-    const long long cap = static_cast<long long>(sm_count()) * 4;
+    long long g = (npix + kHeadTile - 1) / kHeadTile;
+    const long long cap = static_cast<long long>(sm_count()) * 2;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    head_bwd_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(
-        dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
-        reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
-        reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+    if (cout <= 6)
+        head_bwd_kernel<6><<<static_cast<unsigned>(g), 256, 0, stream>>>(
+            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
+            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+    else if (cout <= 8)
+        head_bwd_kernel<8><<<static_cast<unsigned>(g), 256, 0, stream>>>(
+            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
+            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+    else
+        head_bwd_kernel<16><<<static_cast<unsigned>(g), 256, 0, stream>>>(
+            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
+            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -95,6 +95,16 @@ struct hd_net {
     void* wgrad_ws = nullptr;
     size_t wgrad_ws_bytes = 0;
     float* small = nullptr;   // scratch for BN-backward sums / coefficients
+    // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
+    // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
+    Arena wg;
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t ev_next = 0;
+    ~hd_net() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
+    }
 };
 
 static const hd_unit_ptrs kNullUnit{};
@@ -322,13 +332,32 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, int H, int W) {
+// Event recorded on the main stream at the point where a wgrad operand (dY) is complete.
+static cudaEvent_t mark_ready(hd_net* n) {
+    if (n->dry || n->rc != 0) return nullptr;
+    if (n->events.empty()) {
+        n->events.resize(96);
+        for (cudaEvent_t& e : n->events)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                n->rc = fail(HD_ERR_CUDA, "net_backward: cudaEventCreate failed");
+                return nullptr;
+            }
+    }
+    cudaEvent_t e = n->events[n->ev_next++ % n->events.size()];
+    if (cudaEventRecord(e, n->stream) != cudaSuccess) n->rc = fail(HD_ERR_CUDA, "net_backward: cudaEventRecord failed");
+    return e;
+}
+
+// Weight gradient on the side stream, ordered after `ready` (the dY producer) of the main stream.
+static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, int H, int W, cudaEvent_t ready) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
+    if (!n->dry && n->rc == 0 && ready && cudaStreamWaitEvent(n->side, ready, 0) != cudaSuccess)
+        n->rc = fail(HD_ERR_CUDA, "net_backward: cudaStreamWaitEvent failed");
     if (u.kind == 1)
-        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->stream));
+        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->side));
     else
-        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->stream));
+        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->side));
 }
 
 static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H, int W, const bf16* addend) {
@@ -368,16 +397,19 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     const int H = r.H, W = r.W;
     const size_t mark = n->bw.off;
     const size_t bytes_o = act_bytes(B, H, W, r.cout), bytes_i = act_bytes(B, H, W, r.cin);
-    bf16* dY2 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
-    bf16* dYs = r.us >= 0 ? reinterpret_cast<bf16*>(n->bw.alloc(bytes_o)) : nullptr;
+    // dY buffers are wgrad operands read asynchronously by the side stream: bump-only region, never reused
+    bf16* dY2 = reinterpret_cast<bf16*>(n->wg.alloc(bytes_o));
+    bf16* dYs = r.us >= 0 ? reinterpret_cast<bf16*>(n->wg.alloc(bytes_o)) : nullptr;
+    bf16* dY1 = reinterpret_cast<bf16*>(n->wg.alloc(bytes_o));
     bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G);
-    wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W);
+    cudaEvent_t e2 = mark_ready(n);
     bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
-    bf16* dY1 = dY2;  // dY2 is dead after its dgrad / wgrad: reuse the buffer
+    wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W, e2);        // overlaps the BN backward below
+    if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W, e2);
     bn_bwd_unit(n, r.u1, dZ1, r.Z1, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
-    wgrad_unit(n, r.u1, r.X, dY1, B, H, W);
+    cudaEvent_t e1 = mark_ready(n);
     if (r.us < 0) {
         dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
     } else {
@@ -385,7 +417,7 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
         dgrad_unit(n, r.u1, dY1, dXa, B, H, W, nullptr);
         dgrad_unit(n, r.us, dYs, dX, B, H, W, dXa);
     }
-    if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W);
+    wgrad_unit(n, r.u1, r.X, dY1, B, H, W, e1);         // overlaps the next block's BN backward
     n->bw.off = mark;
 }
 
@@ -426,8 +458,9 @@ static void backward_impl(hd_net* n, const float* dlogits) {
             const hd_unit_ptrs& pmp = UP(n, s.u_mp);
             RUN(hd_colsum(dXn, pmp.db, npix4, C, C, n->stream));
             RUN(hd_colsum(dXn, pmf.db, npix4, C, C, n->stream));
-            wgrad_unit(n, s.u_mp, s.pred64, dXn, B, H4, W4);
-            wgrad_unit(n, s.u_mf, s.F2, dXn, B, H4, W4);
+            cudaEvent_t em = mark_ready(n);
+            wgrad_unit(n, s.u_mp, s.pred64, dXn, B, H4, W4, em);
+            wgrad_unit(n, s.u_mf, s.F2, dXn, B, H4, W4, em);
             dpred = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H4, W4, 16)));
             Unit& ump = n->units[s.u_mp];
             RUN(hd_conv2d_igemm(dXn, ump.wpd, dpred, nullptr, nullptr, nullptr, nullptr, nullptr, B, H4, W4, C,
@@ -449,10 +482,11 @@ static void backward_impl(hd_net* n, const float* dlogits) {
         residual_bwd(n, s.neck_res, dF2, dF1, B);
         bf16* dYn = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         bn_bwd_unit(n, s.u_neck, dF1, s.F1, s.Yn, dYn, -1, nullptr, nullptr, nullptr);
+        cudaEvent_t en = mark_ready(n);
         RUN(hd_colsum(dYn, UP(n, s.u_neck).db, npix4, C, C, n->stream));
-        wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4);
         bf16* dHg = dF1;  // dead
         dgrad_unit(n, s.u_neck, dYn, dHg, B, H4, W4, nullptr);
+        wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4, en);
         bf16* dXi = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);
         dXn = dXi;
@@ -468,8 +502,15 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     residual_bwd(n, n->r_pre1, dR1, dZ0, B);
     bf16* dY0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     bn_bwd_unit(n, 0, dZ0, n->Z0, n->Y0, dY0, -1, nullptr, nullptr, nullptr);
+    cudaEvent_t e0 = mark_ready(n);
     RUN(hd_colsum(dY0, UP(n, 0).db, static_cast<long long>(B) * H2 * W2, 64, 64, n->stream));
-    wgrad_unit(n, 0, n->patches, dY0, B, H2, W2);
+    wgrad_unit(n, 0, n->patches, dY0, B, H2, W2, e0);
+    // join: everything the side stream produced (all weight gradients) is ordered before whatever follows on `stream`
+    if (!n->dry && n->rc == 0) {
+        cudaEvent_t done = n->events[n->ev_next++ % n->events.size()];
+        if (cudaEventRecord(done, n->side) != cudaSuccess || cudaStreamWaitEvent(n->stream, done, 0) != cudaSuccess)
+            n->rc = fail(HD_ERR_CUDA, "net_backward: stream join failed");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ planning + entry points
@@ -509,8 +550,9 @@ extern "C" size_t hd_net_workspace_bytes(hd_net* n, int B, int H, int W, int wit
     size_t total = head + ((n->fw.peak + 255) & ~size_t(255));
     if (with_backward) {
         n->bw = Arena();
+        n->wg = Arena();
         backward_impl(n, nullptr);
-        total += (n->bw.peak + 255) & ~size_t(255);
+        total += ((n->bw.peak + 255) & ~size_t(255)) + ((n->wg.peak + 255) & ~size_t(255));
     }
     n->dry = false;
     n->trained_fwd = false;
@@ -544,9 +586,9 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
     n->trained_fwd = training != 0 && n->rc == 0;
     // backward region starts after the forward region
     const size_t fw_end = head + ((n->fw.peak + 255) & ~size_t(255));
-    n->bw = Arena();
-    n->bw.base = reinterpret_cast<uint8_t*>(workspace) + fw_end;
-    n->bw.cap = workspace_bytes > fw_end ? workspace_bytes - fw_end : 0;
+    n->wg = Arena();
+    n->wg.base = reinterpret_cast<uint8_t*>(workspace) + fw_end;
+    n->wg.cap = workspace_bytes > fw_end ? workspace_bytes - fw_end : 0;
     return n->rc;
 }
 
@@ -557,16 +599,20 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     HD_REQUIRE(n->trained_fwd, "net_backward: no training-mode forward pass is pending on this network");
     HD_REQUIRE(reinterpret_cast<uint8_t*>(workspace) == n->persist.base, "net_backward: workspace moved since the forward pass");
     n->up = units; n->stream = stream; n->rc = 0;
-    // capacity check (dry) then run
-    Arena keep = n->bw;
+    if (!n->side && cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(HD_ERR_CUDA, "net_backward: cannot create the weight-gradient stream");
+    // capacity check (dry) then run: [wg: bump-only dY operands][bw: stack-allocated temporaries]
+    uint8_t* region = n->wg.base;
+    const size_t region_cap = n->wg.cap;
     n->dry = true;
+    n->wg = Arena(); n->bw = Arena();
     backward_impl(n, nullptr);
-    const size_t need = n->bw.peak;
-    n->bw = keep;
-    n->bw.off = 0; n->bw.peak = 0;
+    const size_t wg_need = (n->wg.peak + 255) & ~size_t(255), bw_need = n->bw.peak;
     n->dry = false;
-    HD_REQUIRE(need <= n->bw.cap, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)",
-               n->bw.cap, need);
+    n->wg = Arena(); n->wg.base = region; n->wg.cap = region_cap;
+    n->bw = Arena(); n->bw.base = region + wg_need; n->bw.cap = region_cap > wg_need ? region_cap - wg_need : 0;
+    HD_REQUIRE(wg_need + bw_need <= region_cap, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)",
+               region_cap, wg_need + bw_need);
     backward_impl(n, dlogits);
     n->trained_fwd = false;
     return n->rc;

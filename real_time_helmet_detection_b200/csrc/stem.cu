@@ -11,36 +11,57 @@ namespace hd {
 
 constexpr int kStemK = 147, kStemKPad = 192;
 
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                   int W) {
+// One CTA = a TOH x TOW tile of output pixels. The (2*TOH+5) x (2*TOW+5) x 3 input window is staged once in shared
+// memory (zero-filled outside the image = the conv's padding), then every thread emits 16-byte vectors of the patch
+// matrix: consecutive threads write consecutive 8-k vectors of one pixel, so the 384-byte rows are written coalesced.
+constexpr int kTOH = 8, kTOW = 32;
+constexpr int kPH = 2 * kTOH + 5, kPW = 2 * kTOW + 5;
+
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int N, int H, int W) {
+    __shared__ float patch[3][kPH][kPW + 1];
+    __shared__ short koff[kStemKPad];      // k -> offset inside the patch of the pixel at (0,0); -1 for the zero padding
     const int Ho = H >> 1, Wo = W >> 1;
-    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * (kStemKPad / 8);
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int kv = i % (kStemKPad / 8);
-        size_t pix = i / (kStemKPad / 8);
-        const int ox = pix % Wo;
-        const int oy = (pix / Wo) % Ho;
-        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+    const int tiles_x = (Wo + kTOW - 1) / kTOW, tiles_y = (Ho + kTOH - 1) / kTOH;
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+    const int oy0 = ty * kTOH, ox0 = tx * kTOW;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    for (int k = threadIdx.x; k < kStemKPad; k += blockDim.x) {
+        short o = -1;
+        if (k < kStemK) {
+            const int c = k % 3, kk = k / 3, ky = kk / 7, kx = kk - ky * 7;
+            o = static_cast<short>((c * kPH + ky) * (kPW + 1) + kx);
+        }
+        koff[k] = o;
+    }
+    for (int i = threadIdx.x; i < 3 * kPH * kPW; i += blockDim.x) {
+        const int px = i % kPW, py = (i / kPW) % kPH, c = i / (kPW * kPH);
+        const int iy = iy0 + py, ix = ix0 + px;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + iy) * W + ix);
+        patch[c][py][px] = v;
+    }
+    __syncthreads();
+    const float* pbase = &patch[0][0][0];
+    constexpr int kVec = kStemKPad / 8;   // 24 vectors per pixel
+    for (int t = threadIdx.x; t < kTOH * kTOW * kVec; t += blockDim.x) {
+        const int kv = t % kVec, lp = t / kVec;
+        const int lx = lp % kTOW, ly = lp / kTOW;
+        const int oy = oy0 + ly, ox = ox0 + lx;
+        if (oy >= Ho || ox >= Wo) continue;
+        const int pofs = (2 * ly) * (kPW + 1) + 2 * lx;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = kv * 8 + j;
-            float val = 0.f;
-            if (k < kStemK) {
-                const int c = k % 3, kk = k / 3;
-                const int ky = kk / 7, kx = kk - ky * 7;
-                const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                    val = __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + iy) * W + ix);
-            }
-            v[j] = val;
+            const int o = koff[kv * 8 + j];
+            v[j] = o >= 0 ? pbase[o + pofs] : 0.f;
         }
         uint4 u;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        *reinterpret_cast<uint4*>(out + i * 8) = u;
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * kStemKPad + kv * 8) = u;
     }
 }
 
@@ -62,12 +83,11 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat
 extern "C" int hd_stem_im2col(const float* x, void* patches, int N, int H, int W, cudaStream_t stream) {
     using namespace hd;
     HD_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "stem_im2col: shape (%d,3,%d,%d)", N, H, W);
-    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (kStemKPad / 8);
-    size_t g = (nvec + 255) / 256;
-    const size_t cap = static_cast<size_t>(sm_count()) * 16;
-    if (g > cap) g = cap;
-    stem_im2col_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), N,
-                                                                   H, W);
+    const int Ho = H / 2, Wo = W / 2;
+    const long long tiles = static_cast<long long>(N) * ((Ho + kTOH - 1) / kTOH) * ((Wo + kTOW - 1) / kTOW);
+    HD_REQUIRE(tiles < (1ll << 31), "stem_im2col: too many tiles");
+    stem_im2col_kernel<<<static_cast<unsigned>(tiles), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches),
+                                                                        N, H, W);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -49,6 +49,10 @@ int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, 
                     int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                     hd_stream_t stream);
 
+/* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the
+ * halo-reuse M=256 kernel (3x3, block_n 128, map >= 16x16) whenever the shape is eligible. */
+void hd_set_conv_variant(int variant);
+
 /* Weight gradient of the same convs (autograd of hourglass.py:100): grad_w (OIHW fp32 [cout][cin_real][k][k])
  * = (accumulate ? grad_w : 0) + sum_pixels dy[p, co] * x[p + tap, ci].  x nhwc [.., cin], dy nhwc [.., cout],
  * cout in {64,128}, cin in {64,128,192(k=1)}. workspace: hd_conv2d_wgrad_workspace_bytes() bytes.

@@ -63,6 +63,64 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
     return v[0];
 }
 
+// Epilogue of one 128-row accumulator block: TMEM -> registers (32 columns at a time) -> bias / residual addend ->
+// bf16 NHWC store, plus the per-channel sum / sum-of-squares (train-mode BN statistics) into s_stat.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t taddr, bool valid, size_t pix, uint32_t lane,
+                                              float* s_stat, bool do_stats) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
+        }
+        if (p.addend && valid) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.out_cs + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u = __ldg(ap + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    v[q * 8 + 2 * j] += f.x;
+                    v[q * 8 + 2 * j + 1] += f.y;
+                }
+            }
+        }
+        if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                op[q] = u;
+            }
+        }
+        if (do_stats) {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                v[i] = valid ? v[i] : 0.f;
+                sq[i] = v[i] * v[i];
+            }
+            float s1 = warp_transpose_reduce(v, lane);
+            float s2 = warp_transpose_reduce(sq, lane);
+            atomicAdd(&s_stat[c0 + lane], s1);
+            atomicAdd(&s_stat[BLOCK_N + c0 + lane], s2);
+        }
+    }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -184,58 +242,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (BLOCK_N >= 32) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_x32(taddr + c0, r);
-                    tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
-                    }
-                    if (p.addend && valid) {
-                        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.out_cs + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 u = __ldg(ap + q);
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(h[j]);
-                                v[q * 8 + 2 * j] += f.x;
-                                v[q * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                    if (valid) {
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                             pix * p.out_cs + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 u;
-                            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                            op[q] = u;
-                        }
-                    }
-                    if (do_stats) {
-                        float sq[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            v[i] = valid ? v[i] : 0.f;
-                            sq[i] = v[i] * v[i];
-                        }
-                        float s1 = warp_transpose_reduce(v, lane);
-                        float s2 = warp_transpose_reduce(sq, lane);
-                        atomicAdd(&s_stat[c0 + lane], s1);
-                        atomicAdd(&s_stat[BLOCK_N + c0 + lane], s2);
-                    }
-                }
+                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats);
             } else {
                 // BLOCK_N == 16: prediction head (hourglass.py:189-195), fp32 NCHW logits
                 uint32_t r[16];
@@ -312,7 +319,180 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
     return HD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// "Halo" variant for the FLOP-dominant case (3x3, 128 output channels, maps >= 16x16): the generic kernel above
+// re-fetches the activation tile for each of the 9 taps and the weights for every 128-pixel tile, which makes it
+// L2->SM bandwidth bound (measured 14.3 TB/s, ~54 % of the tensor peak). Here a CTA tile is 16x16 pixels (M = 256:
+// two 128-row accumulators sharing every weight tile), and for each dx ONE activation box of 18 rows x 16 columns is
+// loaded; the three dy taps read that tile at a row offset of dy*16 pixels = dy*2048 B (whole 8-row swizzle groups,
+// so only the UMMA descriptor start address moves). L2->SM bytes per FLOP drop 2.3x.
+constexpr int kHARows = 18 * 16;
+constexpr int kHABytes = kHARows * 128;   // 36,864
+constexpr int kHAStages = 3;
+constexpr int kHBBytes = 128 * 128;       // one (tap, 64-channel chunk) weight tile for 128 output channels
+constexpr int kHBStages = 6;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                       const ConvParams p) {
+    constexpr int BLOCK_N = 128;
+    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kHAStages * kHABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kHBStages * kHBBytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kHAStages;
+    uint64_t* b_full = a_empty + kHAStages;
+    uint64_t* b_empty = b_full + kHBStages;
+    uint64_t* tmem_full = b_empty + kHBStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < kHAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kHBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 2 * BLOCK_N) s_stat[threadIdx.x] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int n = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * 16, y0 = ty * 16;
+                for (int dx = 0; dx < 3; ++dx) {
+                    for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                        mbar_wait(&a_empty[sa], pa ^ 1);
+                        mbar_arrive_expect_tx(&a_full[sa], kHABytes);
+                        tma_load_4d(smem_a + sa * kHABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - 1, y0 - 1, n);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(&b_empty[sb], pb ^ 1);
+                            mbar_arrive_expect_tx(&b_full[sb], kHBBytes);
+                            tma_load_3d(smem_b + sb * kHBBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * 3 + dx);
+                            if (++sb == kHBStages) { sb = 0; pb ^= 1; }
+                        }
+                        if (++sa == kHAStages) { sa = 0; pa ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            bool first = true;
+            for (int dx = 0; dx < 3; ++dx) {
+                for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                    mbar_wait(&a_full[sa], pa);
+                    const uint32_t a_addr = smem_u32(smem_a + sa * kHABytes);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + sb * kHBBytes), 0, 1024);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                // rows of accumulator h = tile rows 8h..8h+7, shifted down by dy: (dy + 8h) * 16 pixels
+                                const uint64_t adesc = umma_smem_desc_sw128(a_addr + (dy + 8 * h) * 2048, 0, 1024);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                                              (first && k == 0) ? 0u : 1u);
+                            }
+                            umma_commit(&b_empty[sb]);
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++sb == kHBStages) { sb = 0; pb ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(&a_empty[sa]);
+                    __syncwarp();
+                    if (++sa == kHAStages) { sa = 0; pa ^= 1; }
+                }
+            }
+            if (elect_one()) umma_commit(&tmem_full[acc]);
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        const int row = ew * 32 + (int)lane;
+        const bool do_stats = p.stat_sum != nullptr;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int n = tile / (p.tiles_x * p.tiles_y);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int x = tx * 16 + (row & 15);
+                const int y = ty * 16 + 8 * h + (row >> 4);
+                const bool valid = (x < p.W) && (y < p.H);
+                const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * 128;
+                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+        if (do_stats) {
+            named_bar_sync(1, 128);
+            const int t = threadIdx.x - 128;
+            if (t < p.cout) {
+                atomicAdd(p.stat_sum + t, s_stat[t]);
+                atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+static int g_conv_variant = 0;  // 0 auto, 1 always generic, 2 halo whenever the shape allows (tests)
+
+static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        attr_set = true;
+    }
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    conv_igemm_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tx, tw, p);
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
 }  // namespace hd
+
+// Test / tuning knob: 0 auto, 1 generic kernel only, 2 halo kernel whenever the shape is eligible.
+extern "C" void hd_set_conv_variant(int v) { hd::g_conv_variant = v; }
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
@@ -347,6 +527,17 @@ extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, v
     p.bias = bias; p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
     p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
 
+    // halo variant: 3x3, 128 output channels, map >= 16x16 and enough 16x16 tiles to fill the machine
+    bool halo = false;
+    if (ksize == 3 && block_n == 128 && H >= 16 && W >= 16 && out_mode == 0 && g_conv_variant != 1) {
+        const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
+        halo = g_conv_variant == 2 || ht >= sm_count();
+        if (halo) {
+            tw = 16; th = 18; tn = 1;
+            p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
+            p.num_tiles = ht;
+        }
+    }
     alignas(64) CUtensorMap tmx, tmw;
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -362,6 +553,7 @@ extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, v
         int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);
         if (rc) return rc;
     }
+    if (halo) return launch_conv_halo(tmx, tmw, p, stream);
     if (block_n == 128) return launch_conv<128>(tmx, tmw, p, stream);
     if (block_n == 64) return launch_conv<64>(tmx, tmw, p, stream);
     return launch_conv<16>(tmx, tmw, p, stream);

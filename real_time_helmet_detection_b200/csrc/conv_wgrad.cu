@@ -34,13 +34,18 @@ struct WgradParams {
     int taps;
 };
 
-template <int BLOCK_N>
+// HALO (3x3 kernels on maps with a 16x8 pixel tile): a CTA owns the three dy taps of one dx COLUMN. The X operand of a
+// pixel tile is then ONE box of (8+2) rows x 16 columns at the dx-shifted x coordinate, and the three dy taps are
+// the same shared-memory tile read at a row offset of dy*16 pixels = dy*2048 bytes (a whole number of 8-row swizzle
+// groups, so the UMMA descriptor just starts later). X traffic per tile drops from 3 x 32 KB to 40 KB.
+template <int BLOCK_N, bool HALO>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
-    constexpr int kBBytes = 128 * BLOCK_N * 2;
+    constexpr int kBRows = HALO ? 160 : 128;
+    constexpr int kBBytes = kBRows * BLOCK_N * 2;
     constexpr int kNChunks = BLOCK_N / 64;
-    constexpr int kWgBStages = BLOCK_N > 128 ? 3 : 4;
+    constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
     constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 1, 1);
 
     extern __shared__ uint8_t smem_raw[];
@@ -98,16 +103,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 mbar_arrive_expect_tx(&a_full[ab], kWgABytes);
                 tma_load_4d(smem_a + ab * kWgABytes, &tmap_dy, &a_full[ab], 0, x0, y0, n0);
                 tma_load_4d(smem_a + ab * kWgABytes + 128 * 128, &tmap_dy, &a_full[ab], 64, x0, y0, n0);
-                for (int t = 0; t < p.taps_per_group; ++t) {
-                    const int tap = group * p.taps_per_group + t;
-                    const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                if constexpr (HALO) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
 #pragma unroll
                     for (int c = 0; c < kNChunks; ++c)
-                        tma_load_4d(smem_b + stage * kBBytes + c * 128 * 128, &tmap_x, &full_bar[stage], c * 64,
-                                    x0 + dx, y0 + dy, n0);
+                        tma_load_4d(smem_b + stage * kBBytes + c * kBRows * 128, &tmap_x, &full_bar[stage], c * 64,
+                                    x0 + group - 1, y0 - 1, n0);
                     if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
+                } else {
+                    for (int t = 0; t < p.taps_per_group; ++t) {
+                        const int tap = group * p.taps_per_group + t;
+                        const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
+#pragma unroll
+                        for (int c = 0; c < kNChunks; ++c)
+                            tma_load_4d(smem_b + stage * kBBytes + c * 128 * 128, &tmap_x, &full_bar[stage], c * 64,
+                                        x0 + dx, y0 + dy, n0);
+                        if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -118,6 +133,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
             mbar_wait(&a_full[ab], aphase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem_a + ab * kWgABytes);
+            if constexpr (HALO) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sb = smem_u32(smem_b + stage * kBBytes);
+                    const uint64_t adesc = umma_smem_desc_sw128(sa, 128 * 128, 1024);
+                    const uint64_t bdesc = umma_smem_desc_sw128(sb, kBRows * 128, 1024);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem_base + t * BLOCK_N, adesc + 128 * k, bdesc + 128 * (k + t), kIdesc,
+                                      (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
+            } else
             for (int t = 0; t < p.taps_per_group; ++t) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -149,7 +183,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         for (int t = 0; t < p.taps_per_group; ++t) {
-            const int tap = group * p.taps_per_group + t;
+            const int tap = HALO ? t * p.kw + group : group * p.taps_per_group + t;
             float* dst = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * 128 + row) * BLOCK_N;
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -193,17 +227,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     *g = accumulate ? (*g + s) : s;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HALO>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
-    constexpr int kWgBStages = BLOCK_N > 128 ? 3 : 4;
-    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * 128 * BLOCK_N * 2 + 1024 + 256;
+    constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
+    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HALO ? 160 : 128) * BLOCK_N * 2 + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
+        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, HALO>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set = true;
     }
-    conv_wgrad_kernel<BLOCK_N><<<p.groups * p.ksplit, kWgThreads, smem_bytes, stream>>>(tdy, tx, p);
+    conv_wgrad_kernel<BLOCK_N, HALO><<<p.groups * p.ksplit, kWgThreads, smem_bytes, stream>>>(tdy, tx, p);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -254,6 +288,7 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     p.num_tiles = p.tiles_x * p.tiles_y * ((N + tn - 1) / tn);
     p.ksplit = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
     p.ws = reinterpret_cast<float*>(workspace);
+    const bool halo = ksize == 3 && tw == 16 && th == 8;   // the dy taps become row offsets of one 10-row X tile
 
     alignas(64) CUtensorMap tdy, tx;
     {
@@ -266,13 +301,13 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
-        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)(halo ? th + 2 : th), (uint32_t)tn};
         int rc = make_tmap_bf16(&tx, x, 4, dims, str, box);
         if (rc) return rc;
     }
-    int rc = (cin == 192)   ? launch_wgrad<192>(tdy, tx, p, stream)
-             : (cin == 128) ? launch_wgrad<128>(tdy, tx, p, stream)
-                            : launch_wgrad<64>(tdy, tx, p, stream);
+    int rc = (cin == 192)   ? launch_wgrad<192, false>(tdy, tx, p, stream)
+             : (cin == 128) ? (halo ? launch_wgrad<128, true>(tdy, tx, p, stream) : launch_wgrad<128, false>(tdy, tx, p, stream))
+                            : (halo ? launch_wgrad<64, true>(tdy, tx, p, stream) : launch_wgrad<64, false>(tdy, tx, p, stream));
     if (rc) return rc;
     const int total = p.taps * cout * cin_real;
     wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128,

@@ -181,7 +181,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
                                      const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ ys,
                                      const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
                                      float* __restrict__ sums, size_t npix, int C) {
-    extern __shared__ float red[];  // [3][blockDim.x/cvec rows][C]  -> reduced over rows
+    extern __shared__ float red[];  // [3][C]
     const int cvec = C >> 3;
     const int lane_c = threadIdx.x % cvec;          // which 8-channel vector
     const int row = threadIdx.x / cvec;             // pixel lane inside the block
@@ -214,26 +214,32 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
             if (SECOND) a2[j] += gj * ((y2.v[j] - ms[j]) * rs[j]);
         }
     }
-    float* r0 = red;
-    float* r1 = red + rows * C;
-    float* r2 = red + 2 * rows * C;
+    // block reduction with a tiny shared footprint (3*C floats) so that several of these CTAs can share an SM with a
+    // persistent tcgen05 conv CTA (~194 KB of shared memory) when the executor overlaps them on two streams
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    // lanes l and l^16 (cvec == 16) or l^8, l^16 (cvec == 8) hold the same channels of different pixel rows
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        r0[row * C + c0 + j] = a0[j];
-        r1[row * C + c0 + j] = a1[j];
-        if (SECOND) r2[row * C + c0 + j] = a2[j];
+        for (int o = cvec; o < 32; o <<= 1) {
+            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
+            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
+            if (SECOND) a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o);
+        }
+    }
+    if ((threadIdx.x & 31) < cvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&red[c0 + j], a0[j]);
+            atomicAdd(&red[C + c0 + j], a1[j]);
+            if (SECOND) atomicAdd(&red[2 * C + c0 + j], a2[j]);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int k = 0; k < rows; ++k) {
-            s0 += r0[k * C + c];
-            s1 += r1[k * C + c];
-            if (SECOND) s2 += r2[k * C + c];
-        }
-        atomicAdd(sums + c, s0);
-        atomicAdd(sums + C + c, s1);
-        if (SECOND) atomicAdd(sums + 2 * C + c, s2);
+        atomicAdd(sums + c, red[c]);
+        atomicAdd(sums + C + c, red[C + c]);
+        if (SECOND) atomicAdd(sums + 2 * C + c, red[2 * C + c]);
     }
 }
 
@@ -397,14 +403,17 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += v.v[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[row * C + lane_c * 8 + j] = a[j];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < rows; ++k) s += red[k * C + c];
-        atomicAdd(out + c, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        for (int o = cvec; o < 32; o <<= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    if ((threadIdx.x & 31) < cvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&red[lane_c * 8 + j], a[j]);
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, red[c]);
 }
 
 }  // namespace hd
@@ -481,15 +490,11 @@ extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, cvp y, const float* mean, con
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
-    const size_t smem = 3 * static_cast<size_t>(rows) * C * sizeof(float);
+    const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     if (ys) {
-        static bool set1 = false;
-        if (!set1) { HD_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); set1 = true; }
         bn_bwd_reduce_kernel<true><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, BF(ys), mean_s,
                                                                 rstd_s, sums, static_cast<size_t>(npix), C);
     } else {
-        static bool set0 = false;
-        if (!set0) { HD_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304)); set0 = true; }
         bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, nullptr,
                                                                  nullptr, nullptr, sums, static_cast<size_t>(npix), C);
     }
@@ -558,7 +563,7 @@ extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaS
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
-    colsum_kernel<<<blocks, 256, static_cast<size_t>(rows) * C * sizeof(float), stream>>>(BF(x), out, static_cast<size_t>(npix), C, cs);
+    colsum_kernel<<<blocks, 256, static_cast<size_t>(C) * sizeof(float), stream>>>(BF(x), out, static_cast<size_t>(npix), C, cs);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -119,3 +119,41 @@ def test_head_conv(cuda_device):
     padc = ops.to_nchw(pad).cpu()
     assert _rel_l2(padc[:, :6], ref) <= 3e-3
     assert torch.count_nonzero(padc[:, 6:16]) == 0
+
+
+HALO_CASES = [(2, 32, 32, 128, 128, 3), (1, 64, 48, 128, 128, 3), (1, 40, 24, 128, 128, 3), (2, 16, 16, 64, 128, 3),
+              (3, 17, 33, 128, 128, 3)]
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k", HALO_CASES)
+def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k):
+    """The halo-reuse M=256 kernel (forced) must agree with PyTorch exactly like the generic kernel: forward with bias,
+    residual addend and BN statistics, and dgrad."""
+    from real_time_helmet_detection_b200 import ops, _lib
+    g = torch.Generator().manual_seed(77 + H + W)
+    x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
+    r = _bf16_round(torch.randn(N, cout, H, W, generator=g))
+    w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    bias = torch.randn(cout, generator=g)
+    conv = F.conv2d(x, w, bias, padding=1)
+    ref = conv + r
+    _lib.lib().hd_set_conv_variant(2)
+    try:
+        stats = torch.zeros(2, cout, device=cuda_device)
+        y = ops.conv2d_igemm(ops.to_nhwc(x.to(cuda_device)), ops.pack_weight(w.to(cuda_device)), cout, k,
+                             bias=bias.to(cuda_device), addend=ops.to_nhwc(r.to(cuda_device)), stats=stats)
+        out = ops.to_nchw(y).cpu()
+        if cin == cout:
+            dy = _bf16_round(torch.randn(N, cout, H, W, generator=g))
+            dref = torch.nn.grad.conv2d_input((N, cin, H, W), w, dy, padding=1)
+            dx = ops.to_nchw(ops.conv2d_igemm(ops.to_nhwc(dy.to(cuda_device)), ops.pack_weight(w.to(cuda_device), mode=1),
+                                              cin, k)).cpu()
+    finally:
+        _lib.lib().hd_set_conv_variant(0)
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert _rel_l2(out, ref) <= 3e-3
+    s1, s2 = ref.sum(dim=(0, 2, 3)), (ref * ref).sum(dim=(0, 2, 3))
+    assert torch.allclose(stats[0].cpu(), s1, rtol=1e-3, atol=1e-3 * s2.sqrt().max().item())
+    assert torch.allclose(stats[1].cpu(), s2, rtol=1e-3)
+    if cin == cout:
+        assert _rel_l2(dx, dref) <= 3e-3

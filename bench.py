@@ -205,7 +205,7 @@ def decode_latency(torch, dev, S=1, runs=300):
     api_wall_us: `Prediction.decode` as a user calls it (allocations + launch + the one count read-back sync)."""
     from real_time_helmet_detection_b200.synthetic import synthetic_head
     from real_time_helmet_detection_b200.evaluate import Prediction
-    from real_time_helmet_detection_b200.transform import _decode_call
+    from real_time_helmet_detection_b200.transform import _decode_call, _decode_buffers
     head = torch.from_numpy(synthetic_head(S=S)).to(dev)
     pred = Prediction(None, topk=100, scale_factor=4, conf_th=0.2, nms="nms", nms_th=0.2)
     for _ in range(10):
@@ -213,11 +213,13 @@ def decode_latency(torch, dev, S=1, runs=300):
     B, S_, O, H, W = head.shape
     C, hw = O - 4, H * W
     strides = ((S_ * O * hw, O * hw),) * 3
+    bufs = _decode_buffers(dev, B, S_, C, H, W, 100)
+    off_v, wh_v = head[:, :, C:], head[:, :, C + 2:]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(runs):
-        _decode_call(head, head[:, :, C:], head[:, :, C + 2:], strides, B, S_, C, H, W, 100, 4, 0.2, 0.2, False, True, True)
+        _decode_call(head, off_v, wh_v, strides, B, S_, C, H, W, 100, 4, 0.2, 0.2, False, True, True, bufs=bufs)
     e1.record()
     torch.cuda.synchronize()
     dev_us = e0.elapsed_time(e1) * 1e3 / runs

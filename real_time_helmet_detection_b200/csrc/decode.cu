@@ -172,14 +172,31 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
                     }
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int acc = 0, d = 255;
-                    for (; d > 0; --d) {
-                        if (acc + hist[d] >= remaining) break;
-                        acc += hist[d];
+                if (tid < 32) {
+                    // warp-parallel scan of the 256 bins from the top: lane l owns bins 255-8l .. 248-8l
+                    int cnt[8], sum = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        cnt[j] = hist[255 - (tid * 8 + j)];
+                        sum += cnt[j];
                     }
-                    misc[0] = d;
-                    misc[1] = remaining - acc;
+                    int inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (tid >= o) inc += t;
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, inc >= remaining);
+                    const int owner = hit ? __ffs(hit) - 1 : 31;
+                    if (tid == owner) {
+                        int acc = inc - sum, j = 0;
+                        for (; j < 7; ++j) {
+                            if (acc + cnt[j] >= remaining) break;
+                            acc += cnt[j];
+                        }
+                        misc[0] = 255 - (tid * 8 + j);
+                        misc[1] = remaining - acc;
+                    }
                 }
                 __syncthreads();
                 prefix |= static_cast<unsigned>(misc[0]) << shift;

@@ -403,13 +403,15 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     bf16* dY1 = reinterpret_cast<bf16*>(n->wg.alloc(bytes_o));
     bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G);
-    cudaEvent_t e2 = mark_ready(n);
     bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
-    wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W, e2);        // overlaps the BN backward below
+    // The readiness event is recorded AFTER the dgrad launch on purpose: dgrad and wgrad are both persistent
+    // tensor-core kernels that cannot share an SM, so the wgrad should start when the dgrad ends - exactly when the
+    // HBM-bound BN-backward kernels below start on the main stream and can co-run with it.
+    cudaEvent_t e2 = mark_ready(n);
+    wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W, e2);
     if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W, e2);
     bn_bwd_unit(n, r.u1, dZ1, r.Z1, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
-    cudaEvent_t e1 = mark_ready(n);
     if (r.us < 0) {
         dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
     } else {
@@ -417,6 +419,7 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
         dgrad_unit(n, r.u1, dY1, dXa, B, H, W, nullptr);
         dgrad_unit(n, r.us, dYs, dX, B, H, W, dXa);
     }
+    cudaEvent_t e1 = mark_ready(n);
     wgrad_unit(n, r.u1, r.X, dY1, B, H, W, e1);         // overlaps the next block's BN backward
     n->bw.off = mark;
 }
@@ -482,10 +485,10 @@ static void backward_impl(hd_net* n, const float* dlogits) {
         residual_bwd(n, s.neck_res, dF2, dF1, B);
         bf16* dYn = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         bn_bwd_unit(n, s.u_neck, dF1, s.F1, s.Yn, dYn, -1, nullptr, nullptr, nullptr);
-        cudaEvent_t en = mark_ready(n);
         RUN(hd_colsum(dYn, UP(n, s.u_neck).db, npix4, C, C, n->stream));
         bf16* dHg = dF1;  // dead
         dgrad_unit(n, s.u_neck, dYn, dHg, B, H4, W4, nullptr);
+        cudaEvent_t en = mark_ready(n);
         wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4, en);
         bf16* dXi = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);

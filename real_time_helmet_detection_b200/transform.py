@@ -16,18 +16,19 @@ from . import _lib
 from ._lib import ptr, stream, check
 
 
+def _decode_buffers(dev, B, S, C, H, W, topk):
+    n = S * topk
+    return (torch.empty((B, n, 4), dtype=torch.float32, device=dev), torch.empty((B, n), dtype=torch.int64, device=dev),
+            torch.empty((B, n), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+            torch.empty((_lib.lib().hd_decode_scratch_bytes(B, C, H, W),), dtype=torch.uint8, device=dev))
+
+
 def _decode_call(heat, off, wh, strides, B, S, C, H, W, topk, scale_factor, conf_th, nms_th, normalized,
-                 apply_sigmoid, do_nms):
-    dev = heat.device
+                 apply_sigmoid, do_nms, bufs=None):
     L = _lib.lib()
     if topk > C * H * W:
         raise RuntimeError("selected index k out of range")
-    n = S * topk
-    boxes = torch.empty((B, n, 4), dtype=torch.float32, device=dev)
-    clss = torch.empty((B, n), dtype=torch.int64, device=dev)
-    scores = torch.empty((B, n), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    scratch = torch.empty((L.hd_decode_scratch_bytes(B, C, H, W),), dtype=torch.uint8, device=dev)
+    boxes, clss, scores, counts, scratch = bufs if bufs is not None else _decode_buffers(heat.device, B, S, C, H, W, topk)
     (bh, sh), (bo, so), (bw, sw) = strides
     check(L.hd_decode_nms(ptr(heat), bh, sh, ptr(off), bo, so, ptr(wh), bw, sw, B, S, C, H, W, int(topk),
                           float(scale_factor), float(conf_th), float(nms_th), int(bool(normalized)),

@@ -126,9 +126,10 @@ int hd_loss_backward(const float* hm, long long hm_bs, const float* off, long lo
 
 /* ------------------------------------------------------------------ decode (transform.py:73-110, evaluate.py:126-182) */
 
-size_t hd_decode_scratch_bytes(int B, int C, int H, int W);
-/* One CTA per image: per stack sigmoid (apply_sigmoid) + 3x3 peak test + joint top-k + gather + boxes + threshold,
- * then (do_nms) class-agnostic hard NMS over the concatenated stacks. heat/off/wh: fp32 planes with batch/stack
+size_t hd_decode_scratch_bytes(int B, int S, int C, int H, int W);
+/* Two launches for the whole batch: (1) grid-wide sigmoid (apply_sigmoid) + 3x3 peak test + candidate compaction,
+ * (2) one CTA per image: per stack exact joint top-k + gather + boxes + threshold, then (do_nms) class-agnostic hard
+ * NMS over the concatenated stacks. heat/off/wh: fp32 planes with batch/stack
  * strides. Outputs: boxes [B][S*topk][4] fp32, cls [B][S*topk] int64, scores [B][S*topk] fp32, count [B] int32. */
 int hd_decode_nms(const float* heat, long long bs_heat, long long ss_heat, const float* off, long long bs_off,
                   long long ss_off, const float* wh, long long bs_wh, long long ss_wh, int B, int S, int C, int H,

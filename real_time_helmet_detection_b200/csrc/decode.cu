@@ -1,23 +1,31 @@
-// Fused CenterNet decode + NMS, one CTA per image, no host synchronisation.
+// Fused CenterNet decode + NMS without any host synchronisation.
 // Reference: transform.py:73-110 `hm2box` and evaluate.py:126-182 `Prediction.forward` /
 // `nonmaximum_supression` (torchvision.ops.nms semantics, class-agnostic).
 //
-// Per stack: head activation (sigmoid) -> 3x3 equality peak test -> joint top-k over (C,H,W) by radix select
-// -> bitonic sort of the k survivors -> offset/size gather + box assembly -> `score >= conf_th` prefix.
-// Then over the concatenated stacks: stable sort by score, all-pairs IoU bit-matrix in shared memory,
-// serial sweep by one warp, compacted output in score order.
+// Two launches for the whole batch:
+//   1. decode_peaks_kernel  (grid over all pixels of all images / stacks / classes): head activation (sigmoid),
+//      3x3 equality peak test, and compaction of the positive peaks into a per-(image, stack) candidate list of
+//      64-bit keys  (order-preserving score bits << 32 | ~flat_index)  with one warp-aggregated atomic per warp.
+//      Because the reference applies `score >= conf_th` AFTER top-k, and a threshold commutes with taking a sorted
+//      prefix, peaks below a positive conf_th are dropped right here (typically 2,900 -> 50 candidates).
+//   2. decode_select_nms_kernel (one CTA per image): per stack, exact top-k of the candidate keys (8-bit radix
+//      select with early exit, only when there are more than k), rank sort of the <= k survivors, offset/size gather,
+//      box assembly in the reference's fp32 operation order, threshold prefix; then over the concatenated stacks a
+//      stable sort by score, the all-pairs IoU bit matrix in shared memory, a serial sweep by one warp and the
+//      compacted output in score order.
 //
-// Determinism: equal scores are ordered by ascending flat index (top-k) / ascending candidate position (NMS),
-// the tie-break the oracle (oracle/decode_ref.py) fixes too. Box arithmetic follows the reference's operation
-// order in fp32 without FMA contraction so coordinates are bit-identical.
-// Heat-map values must be >= 0 (probabilities or GT heat-maps), as in every reference call site.
+// Determinism: keys are unique, so the result does not depend on the order in which candidates were appended; equal
+// scores are ordered by ascending flat index (top-k) / ascending candidate position (NMS) - the tie-break the oracle
+// (oracle/decode_ref.py) fixes too. Zero-score fillers (only kept when conf_th <= 0, as in the reference) are the
+// lowest flat indices that are not positive peaks. Box arithmetic uses __f*_rn intrinsics (no FMA contraction) so
+// coordinates are bit-identical to the reference. Heat-map values must be >= 0 (probabilities / GT heat-maps).
 #include "hd_common.h"
 
 namespace hd {
 
-constexpr int kDecThreads = 1024;
-constexpr int kMaxCand = 1024;          // S * topk upper bound
-constexpr int kBigFloats = 32768;       // 128 KB region: score map (when it fits) / NMS bit matrix
+constexpr int kSelThreads = 1024;
+constexpr int kMaxCand = 1024;            // S * topk upper bound (fused NMS limit)
+constexpr int kNmsWords = kMaxCand / 64;  // 16
 
 struct DecodeArgs {
     const float* heat; const float* off; const float* wh;
@@ -25,7 +33,10 @@ struct DecodeArgs {
     int B, S, C, H, W, K;
     float scale_factor, conf_th, nms_th;
     int normalized, apply_sigmoid, do_nms;
-    float* scratch;        // [B][C*H*W] floats, used when the map does not fit the shared region
+    // scratch (per image-stack pair p = b*S + s)
+    int* cand_count;                 // [B*S]
+    unsigned long long* cand_keys;   // [B*S][C*H*W]
+    unsigned char* is_pos;           // [B*S][C*H*W]  (written only when fillers may be needed)
     float* out_boxes;      // [B][S*K][4]
     long long* out_cls;    // [B][S*K]
     float* out_scores;     // [B][S*K]
@@ -34,12 +45,68 @@ struct DecodeArgs {
 
 __device__ __forceinline__ float dsigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
-__device__ __forceinline__ unsigned fkey(float v) {  // order-preserving map for v >= 0 (and general floats)
+__device__ __forceinline__ unsigned fkey(float v) {  // order-preserving map float -> uint
     unsigned u = __float_as_uint(v);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
 
-// Block-wide exclusive scan of one int per thread (1024 threads); returns the exclusive prefix, *total = block sum.
+// ------------------------------------------------------------------------------------------------ kernel 1
+// grid = (ceil(W/32), ceil(H/8), B*S*C), block = (32, 8): one thread per heat-map element.
+__global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = blockIdx.z;
+    const int c = z % a.C, p = z / a.C;          // p = b*S + s
+    const int b = p / a.S, s = p - b * a.S;
+    const int HW = a.H * a.W;
+    const float* pl = a.heat + b * a.bs_heat + s * a.ss_heat + static_cast<long long>(c) * HW;
+    const bool inside = x < a.W && y < a.H;
+    const bool fill = !(a.conf_th > 0.f);
+    bool take = false;
+    float me = 0.f;
+    if (inside) {
+        me = pl[y * a.W + x];
+        if (a.apply_sigmoid) me = dsigmoid(me);
+        float m = me;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= a.H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if ((dy == 0 && dx == 0) || xx < 0 || xx >= a.W) continue;
+                float v = pl[yy * a.W + xx];
+                if (a.apply_sigmoid) v = dsigmoid(v);
+                m = fmaxf(m, v);
+            }
+        }
+        const bool pos_peak = (m == me) && me > 0.f;
+        if (fill) a.is_pos[static_cast<size_t>(p) * a.C * HW + static_cast<size_t>(c) * HW + y * a.W + x] = pos_peak;
+        take = pos_peak && (fill || me >= a.conf_th);
+    }
+    // warp-aggregated append
+    const unsigned lane = threadIdx.x;   // blockDim.x == 32: one warp per row of the block
+    const unsigned vote = __ballot_sync(0xffffffffu, take);
+    if (vote) {
+        int base = 0;
+        const int leader = __ffs(vote) - 1;
+        if (static_cast<int>(lane) == leader) base = atomicAdd(a.cand_count + p, __popc(vote));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (take) {
+            const int slot = base + __popc(vote & ((1u << lane) - 1u));
+            const unsigned idx = static_cast<unsigned>(c) * HW + y * a.W + x;
+            a.cand_keys[static_cast<size_t>(p) * a.C * HW + slot] =
+                (static_cast<unsigned long long>(fkey(me)) << 32) | (0xFFFFFFFFu - idx);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel 2
+// Block-wide exclusive scan of one int per thread (1024 threads).
 __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = v;
@@ -59,7 +126,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
             int t = __shfl_up_sync(0xffffffffu, si, o);
             if (lane >= o) si += t;
         }
-        warp_sums[lane] = si - s;          // exclusive warp offsets
+        warp_sums[lane] = si - s;
         if (lane == 31) warp_sums[32] = si;
     }
     __syncthreads();
@@ -67,113 +134,81 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
     return warp_sums[w] + inc - v;
 }
 
-// In-place bitonic sort, descending, of n (power of two <= 1024) 64-bit keys in shared memory.
-__device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            const int i = threadIdx.x;
-            if (i < n) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long a = keys[i], b = keys[l];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
-                }
-            }
-        }
+// Descending rank sort of n <= 1024 unique 64-bit keys: thread i places keys[i] at its rank. src -> dst.
+__device__ __forceinline__ void rank_sort_desc(const unsigned long long* src, unsigned long long* dst, int n) {
+    __syncthreads();
+    if (threadIdx.x < n) {
+        const unsigned long long me = src[threadIdx.x];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += src[j] > me;
+        dst[rank] = me;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char dsm[];
-    float* big = reinterpret_cast<float*>(dsm);                                   // kBigFloats floats
-    unsigned* pk_s = reinterpret_cast<unsigned*>(big + kBigFloats);               // kBigFloats/32 words
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(pk_s + kBigFloats / 32);  // 1024
-    float* cbox = reinterpret_cast<float*>(keys + 1024);                          // [kMaxCand][4]
-    float* cscore = cbox + 4 * kMaxCand;                                          // [kMaxCand]
-    int* ccls = reinterpret_cast<int*>(cscore + kMaxCand);                        // [kMaxCand]
-    int* order = ccls + kMaxCand;                                                 // [kMaxCand]
-    int* hist = order + kMaxCand;                                                 // 256
-    int* wsum = hist + 256;                                                       // 33
-    int* misc = wsum + 40;                                                        // small scalars
+    unsigned long long* mat = reinterpret_cast<unsigned long long*>(dsm);             // [kMaxCand][kNmsWords] 128 KB
+    unsigned long long* keys = mat + kMaxCand * kNmsWords;                              // [1024] selected
+    unsigned long long* sorted = keys + 1024;                                           // [1024]
+    float* cbox = reinterpret_cast<float*>(sorted + 1024);                              // [kMaxCand][4]
+    float* cscore = cbox + 4 * kMaxCand;
+    int* ccls = reinterpret_cast<int*>(cscore + kMaxCand);
+    int* order = ccls + kMaxCand;
+    int* hist = order + kMaxCand;    // 256
+    int* wsum = hist + 256;          // 33 (+pad)
+    int* misc = wsum + 40;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int HW = a.H * a.W;
     const int CHW = a.C * HW;
-    const bool in_smem = CHW <= kBigFloats;
-    float* v = in_smem ? big : a.scratch + static_cast<size_t>(b) * CHW;
-    // peak bits: shared when they fit, else reuse the tail of the global scratch row (as floats are 32-bit too)
-    unsigned* pk = in_smem ? pk_s : reinterpret_cast<unsigned*>(a.scratch + static_cast<size_t>(a.B) * CHW) +
-                                        static_cast<size_t>(b) * ((CHW + 31) / 32);
-    const int CHW_pad = (CHW + 31) & ~31;
-    int ncand = 0;  // candidates gathered so far (uniform across the block)
+    const int K = a.K;
+    const bool fill = !(a.conf_th > 0.f);
+    int ncand = 0;
 
     for (int s = 0; s < a.S; ++s) {
-        const float* heat = a.heat + b * a.bs_heat + s * a.ss_heat;
+        const int p = b * a.S + s;
         const float* offp = a.off + b * a.bs_off + s * a.ss_off;
         const float* whp = a.wh + b * a.bs_wh + s * a.ss_wh;
-        // ---- 1. activation
-        for (int i = tid; i < CHW; i += kDecThreads) {
-            float x = heat[i];
-            v[i] = a.apply_sigmoid ? dsigmoid(x) : x;
-        }
-        __syncthreads();
-        // ---- 2. peak test (equality with the 3x3 max, -inf padding) + count of positive peaks
-        int my_pos = 0;
-        for (int i = tid; i < CHW_pad; i += kDecThreads) {
-            bool peak = false;
-            if (i < CHW) {
-                const int c = i / HW, r = i - c * HW;
-                const int y = r / a.W, x = r - y * a.W;
-                const float me = v[i];
-                float m = me;
-                const float* pl = v + c * HW;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = y + dy;
-                    if (yy < 0 || yy >= a.H) continue;
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int xx = x + dx;
-                        if (xx < 0 || xx >= a.W) continue;
-                        m = fmaxf(m, pl[yy * a.W + xx]);
-                    }
+        const unsigned long long* ck = a.cand_keys + static_cast<size_t>(p) * CHW;
+        const int n = min(a.cand_count[p], CHW);
+        int nsel;
+        if (n <= K) {
+            for (int i = tid; i < n; i += kSelThreads) keys[i] = ck[i];
+            nsel = n;
+            if (fill && n < K) {
+                // zero-score fillers: the lowest flat indices that are not positive peaks, in ascending order
+                const unsigned char* isp = a.is_pos + static_cast<size_t>(p) * CHW;
+                const int need = K - n;
+                int taken = 0;
+                for (int base = 0; base < CHW && taken < need; base += kSelThreads) {
+                    const int i = base + tid;
+                    const int flag = (i < CHW) && !isp[i];
+                    int tot;
+                    const int rank = taken + block_excl_scan(flag, wsum, &tot);
+                    if (flag && rank < need)
+                        keys[n + rank] = (static_cast<unsigned long long>(fkey(0.f)) << 32) |
+                                         (0xFFFFFFFFu - static_cast<unsigned>(i));
+                    taken += tot;
                 }
-                peak = (m == me);
-                if (peak && me > 0.f) ++my_pos;
+                nsel = K;
             }
-            const unsigned w = __ballot_sync(0xffffffffu, peak);
-            if ((tid & 31) == 0) pk[i >> 5] = w;
-        }
-        int npos;
-        block_excl_scan(my_pos, wsum, &npos);
-        // peak-map value of element i: pv = peak ? v[i] : 0 ; only pv > 0 take part in the radix select
-        const bool want_fill = !(a.conf_th > 0.f);     // zero-score fillers survive only when conf_th <= 0
-        const int K = a.K;
-        unsigned T = 0x80000000u;                      // key(0.0f)
-        int need_eq = 0;                               // how many elements with key == T to take
-        int n_gt;                                      // how many elements with key > T
-        if (npos >= K) {
-            unsigned prefix = 0;
+        } else {
+            // exact k-th largest 64-bit key by 8-bit radix select (keys are unique); stop as soon as a bin is taken whole
+            unsigned long long prefix = 0ull;
             int remaining = K;
-            for (int pass = 0; pass < 4; ++pass) {
-                const int shift = 24 - 8 * pass;
+            int shift = 56;
+            for (; shift >= 0; shift -= 8) {
                 if (tid < 256) hist[tid] = 0;
                 __syncthreads();
-                for (int i = tid; i < CHW; i += kDecThreads) {
-                    const float val = v[i];
-                    if (val > 0.f && ((pk[i >> 5] >> (i & 31)) & 1u)) {
-                        const unsigned key = fkey(val);
-                        if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
-                            atomicAdd(&hist[(key >> shift) & 255u], 1);
-                    }
+                for (int i = tid; i < n; i += kSelThreads) {
+                    const unsigned long long key = ck[i];
+                    if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                        atomicAdd(&hist[static_cast<unsigned>(key >> shift) & 255u], 1);
                 }
                 __syncthreads();
                 if (tid < 32) {
-                    // warp-parallel scan of the 256 bins from the top: lane l owns bins 255-8l .. 248-8l
                     int cnt[8], sum = 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -196,86 +231,31 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
                         }
                         misc[0] = 255 - (tid * 8 + j);
                         misc[1] = remaining - acc;
+                        misc[4] = cnt[j];
                     }
                 }
                 __syncthreads();
-                prefix |= static_cast<unsigned>(misc[0]) << shift;
+                prefix |= static_cast<unsigned long long>(misc[0]) << shift;
                 remaining = misc[1];
+                const bool whole_bin = misc[4] == remaining;
                 __syncthreads();
+                if (whole_bin) break;     // every key with this prefix is selected: threshold = prefix (low bits 0)
             }
-            T = prefix;
-            need_eq = remaining;
-            n_gt = K - need_eq;
-        } else {
-            n_gt = npos;
-            need_eq = want_fill ? (K - npos) : 0;
-        }
-        // ---- 3. collect: everything with key > T (unordered), then the first need_eq elements with key == T
-        if (tid == 0) { misc[2] = 0; misc[3] = 0; }
-        __syncthreads();
-        int my_eq = 0;
-        for (int i = tid; i < CHW; i += kDecThreads) {
-            const float val = v[i];
-            const bool peak = (pk[i >> 5] >> (i & 31)) & 1u;
-            const float pv = (peak && val > 0.f) ? val : 0.f;
-            const unsigned key = fkey(pv);
-            if (key > T) {
-                const int slot = atomicAdd(&misc[2], 1);
-                keys[slot] = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i));
-            } else if (key == T) {
-                ++my_eq;
+            if (tid == 0) misc[2] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += kSelThreads) {
+                const unsigned long long key = ck[i];
+                if (key >= prefix) keys[atomicAdd(&misc[2], 1)] = key;
             }
+            nsel = K;
         }
-        int total_eq;
-        block_excl_scan(my_eq, wsum, &total_eq);
-        if (need_eq > 0) {
-            if (total_eq == need_eq) {
-                for (int i = tid; i < CHW; i += kDecThreads) {
-                    const float val = v[i];
-                    const bool peak = (pk[i >> 5] >> (i & 31)) & 1u;
-                    const float pv = (peak && val > 0.f) ? val : 0.f;
-                    if (fkey(pv) == T) {
-                        const int slot = n_gt + atomicAdd(&misc[3], 1);
-                        keys[slot] = (static_cast<unsigned long long>(T) << 32) |
-                                     (0xFFFFFFFFu - static_cast<unsigned>(i));
-                    }
-                }
-            } else {
-                // ordered selection: lowest indices first (block scan per 1024-element stripe)
-                int taken = 0;
-                for (int base = 0; base < CHW && taken < need_eq; base += kDecThreads) {
-                    const int i = base + tid;
-                    int flag = 0;
-                    if (i < CHW) {
-                        const float val = v[i];
-                        const bool peak = (pk[i >> 5] >> (i & 31)) & 1u;
-                        const float pv = (peak && val > 0.f) ? val : 0.f;
-                        flag = fkey(pv) == T;
-                    }
-                    int tot;
-                    const int rank = taken + block_excl_scan(flag, wsum, &tot);
-                    if (flag && rank < need_eq)
-                        keys[n_gt + rank] = (static_cast<unsigned long long>(T) << 32) |
-                                            (0xFFFFFFFFu - static_cast<unsigned>(i));
-                    taken += tot;
-                }
-            }
-        }
-        __syncthreads();
-        const int nsel = n_gt + need_eq;               // <= K
-        int npad = 1;
-        while (npad < nsel) npad <<= 1;
-        if (tid >= nsel && tid < npad) keys[tid] = 0ull;
-        __syncthreads();
-        bitonic_desc(keys, npad);
-        // ---- 4. gather + boxes + threshold (kept entries are a prefix because scores are sorted)
+        rank_sort_desc(keys, sorted, nsel);
+        // gather + boxes + threshold (kept entries are a prefix because scores are sorted)
         int keep = 0;
         if (tid < nsel) {
-            const unsigned long long kk = keys[tid];
+            const unsigned long long kk = sorted[tid];
             const int idx = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(kk & 0xFFFFFFFFull));
-            const float val = v[idx];
-            const bool peak = (pk[idx >> 5] >> (idx & 31)) & 1u;
-            const float score = (peak && val > 0.f) ? val : 0.f;
+            const float score = fkey_inv(static_cast<unsigned>(kk >> 32));
             const int cls = idx / HW, r = idx - cls * HW;
             const int y = r / a.W, x = r - y * a.W;
             float xo = offp[r], yo = offp[HW + r], ws = whp[r], hs = whp[HW + r];
@@ -307,11 +287,11 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
 
     // ------------------------------------------------------------------------------------------------ NMS
     const int N = ncand;
-    float* ob = a.out_boxes + static_cast<size_t>(b) * a.S * a.K * 4;
-    long long* oc = a.out_cls + static_cast<size_t>(b) * a.S * a.K;
-    float* os = a.out_scores + static_cast<size_t>(b) * a.S * a.K;
+    float* ob = a.out_boxes + static_cast<size_t>(b) * a.S * K * 4;
+    long long* oc = a.out_cls + static_cast<size_t>(b) * a.S * K;
+    float* os = a.out_scores + static_cast<size_t>(b) * a.S * K;
     if (!a.do_nms) {
-        for (int i = tid; i < N; i += kDecThreads) {
+        for (int i = tid; i < N; i += kSelThreads) {
             ob[4 * i] = cbox[4 * i]; ob[4 * i + 1] = cbox[4 * i + 1];
             ob[4 * i + 2] = cbox[4 * i + 2]; ob[4 * i + 3] = cbox[4 * i + 3];
             oc[i] = ccls[i];
@@ -320,21 +300,19 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
         if (tid == 0) a.out_count[b] = N;
         return;
     }
-    // stable sort by descending score (ties: ascending candidate position)
-    int npad = 1;
-    while (npad < N) npad <<= 1;
-    if (tid < npad)
-        keys[tid] = tid < N ? ((static_cast<unsigned long long>(fkey(cscore[tid])) << 32) |
-                               (0xFFFFFFFFu - static_cast<unsigned>(tid)))
-                            : 0ull;
-    __syncthreads();
-    if (a.S > 1) bitonic_desc(keys, npad);
-    if (tid < N) order[tid] = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(keys[tid] & 0xFFFFFFFFull));
+    // stable sort by descending score (ties: ascending candidate position); already sorted for one stack
+    if (a.S > 1) {
+        if (tid < N)
+            keys[tid] = (static_cast<unsigned long long>(fkey(cscore[tid])) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(tid));
+        rank_sort_desc(keys, sorted, N);
+        if (tid < N) order[tid] = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(sorted[tid] & 0xFFFFFFFFull));
+    } else if (tid < N) {
+        order[tid] = tid;
+    }
     __syncthreads();
     // suppression bit matrix: bit j of row i set <=> j > i (in sorted order) and IoU(i, j) > nms_th
     const int words = (N + 63) >> 6;
-    unsigned long long* mat = reinterpret_cast<unsigned long long*>(big);   // [N][words] <= 1024*16*8 = 128 KB
-    for (int t = tid; t < N * words; t += kDecThreads) {
+    for (int t = tid; t < N * words; t += kSelThreads) {
         const int i = t / words, wj = t - i * words;
         const float* bi = cbox + 4 * order[i];
         const float ax1 = bi[0], ay1 = bi[1], ax2 = bi[2], ay2 = bi[3];
@@ -355,7 +333,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
         mat[t] = bits;
     }
     __syncthreads();
-    // serial sweep by warp 0: lane l owns removed-word l (N <= 1024 -> <= 16 words)
+    // serial sweep by warp 0: lane l owns removed-word l
     if (tid < 32) {
         unsigned long long removed = 0ull;
         int nk = 0;
@@ -377,15 +355,18 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_nms_kernel(const Decode
     }
 }
 
-constexpr size_t kDecSmem = kBigFloats * 4 + kBigFloats / 8 + 1024 * 8 + kMaxCand * (16 + 4 + 4 + 4) + 256 * 4 +
-                            40 * 4 + 64;
+constexpr size_t kSelSmem = static_cast<size_t>(kMaxCand) * kNmsWords * 8 + 2 * 1024 * 8 +
+                            kMaxCand * (16 + 4 + 4 + 4) + 256 * 4 + 40 * 4 + 64;
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 }  // namespace hd
 
-extern "C" size_t hd_decode_scratch_bytes(int B, int C, int H, int W) {
-    const size_t chw = static_cast<size_t>(C) * H * W;
-    if (chw <= static_cast<size_t>(hd::kBigFloats)) return 16;
-    return static_cast<size_t>(B) * (chw + (chw + 31) / 32) * sizeof(float);
+// scratch layout: [counts: B*S ints][keys: B*S*CHW u64][is_pos: B*S*CHW u8]
+extern "C" size_t hd_decode_scratch_bytes(int B, int S, int C, int H, int W) {
+    using namespace hd;
+    const size_t chw = static_cast<size_t>(C) * H * W, ps = static_cast<size_t>(B) * S;
+    return align256(ps * sizeof(int)) + align256(ps * chw * 8) + align256(ps * chw) + 256;
 }
 
 // See include/hd_b200.h.
@@ -403,21 +384,32 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
                static_cast<long long>(C) * H * W);
     HD_REQUIRE(static_cast<long long>(S) * topk <= kMaxCand, "decode: S*topk=%d exceeds the fused limit %d",
                S * topk, kMaxCand);
+    HD_REQUIRE(static_cast<long long>(B) * S * C <= 65535, "decode: B*S*C=%lld exceeds the grid limit",
+               static_cast<long long>(B) * S * C);
+    HD_REQUIRE(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "decode: scratch must be 8-byte aligned");
     DecodeArgs a{};
     a.heat = heat; a.off = off; a.wh = wh;
     a.bs_heat = bs_heat; a.ss_heat = ss_heat; a.bs_off = bs_off; a.ss_off = ss_off; a.bs_wh = bs_wh; a.ss_wh = ss_wh;
     a.B = B; a.S = S; a.C = C; a.H = H; a.W = W; a.K = topk;
     a.scale_factor = scale_factor; a.conf_th = conf_th; a.nms_th = nms_th;
     a.normalized = normalized; a.apply_sigmoid = apply_sigmoid; a.do_nms = do_nms;
-    a.scratch = reinterpret_cast<float*>(scratch);
+    const size_t chw = static_cast<size_t>(C) * H * W, ps = static_cast<size_t>(B) * S;
+    unsigned char* sp = reinterpret_cast<unsigned char*>(scratch);
+    a.cand_count = reinterpret_cast<int*>(sp);
+    a.cand_keys = reinterpret_cast<unsigned long long*>(sp + align256(ps * sizeof(int)));
+    a.is_pos = sp + align256(ps * sizeof(int)) + align256(ps * chw * 8);
     a.out_boxes = out_boxes; a.out_cls = out_cls; a.out_scores = out_scores; a.out_count = out_count;
+    HD_CHECK_CUDA(cudaMemsetAsync(a.cand_count, 0, ps * sizeof(int), stream));
+    dim3 grid((W + 31) / 32, (H + 7) / 8, static_cast<unsigned>(ps * C));
+    decode_peaks_kernel<<<grid, dim3(32, 8), 0, stream>>>(a);
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     static bool attr_set = false;
     if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kDecSmem)));
+        HD_CHECK_CUDA(cudaFuncSetAttribute(decode_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSelSmem)));
         attr_set = true;
     }
-    decode_nms_kernel<<<B, kDecThreads, kDecSmem, stream>>>(a);
+    decode_select_nms_kernel<<<B, kSelThreads, kSelSmem, stream>>>(a);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -15,6 +15,7 @@
 // All launches go to one stream; nothing synchronises with the host.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -604,6 +605,9 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     n->up = units; n->stream = stream; n->rc = 0;
     if (!n->side && cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) != cudaSuccess)
         return fail(HD_ERR_CUDA, "net_backward: cannot create the weight-gradient stream");
+    static const bool serial = getenv("HD_SERIAL_WGRAD") != nullptr;   // debug knob: wgrad on the main stream
+    cudaStream_t side_keep = n->side;
+    if (serial) n->side = stream;
     // capacity check (dry) then run: [wg: bump-only dY operands][bw: stack-allocated temporaries]
     uint8_t* region = n->wg.base;
     const size_t region_cap = n->wg.cap;
@@ -617,6 +621,7 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     HD_REQUIRE(wg_need + bw_need <= region_cap, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)",
                region_cap, wg_need + bw_need);
     backward_impl(n, dlogits);
+    n->side = side_keep;
     n->trained_fwd = false;
     return n->rc;
 }

@@ -20,7 +20,7 @@ def _decode_buffers(dev, B, S, C, H, W, topk):
     n = S * topk
     return (torch.empty((B, n, 4), dtype=torch.float32, device=dev), torch.empty((B, n), dtype=torch.int64, device=dev),
             torch.empty((B, n), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
-            torch.empty((_lib.lib().hd_decode_scratch_bytes(B, C, H, W),), dtype=torch.uint8, device=dev))
+            torch.empty((_lib.lib().hd_decode_scratch_bytes(B, S, C, H, W),), dtype=torch.uint8, device=dev))
 
 
 def _decode_call(heat, off, wh, strides, B, S, C, H, W, topk, scale_factor, conf_th, nms_th, normalized,

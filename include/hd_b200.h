@@ -95,13 +95,16 @@ int hd_maxpool2(const void* x, void* y, int N, int H, int W, int C, hd_stream_t 
 int hd_upsample2_add(const void* up1, const void* low, void* out, int N, int H, int W, int C,
                      hd_stream_t stream);                                                         /* :147,:156 */
 /* backward counterparts */
-int hd_bn_bwd_reduce(const void* dout, const void* out, const void* y, const float* mean, const float* rstd,
+/* g = dout * relu_mask; mask = (out > 0), or, when out == NULL, (y*act_scale + act_shift > 0) recomputed from y. */
+int hd_bn_bwd_reduce(const void* dout, const void* out, const float* act_scale, const float* act_shift,
+                     const void* y, const float* mean, const float* rstd,
                      const void* ys, const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
                      hd_stream_t stream);
 int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
                        const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
                        hd_stream_t stream);
-int hd_bn_bwd_apply(const void* dout, const void* out, const void* y, const float* coef, void* dy, const void* ys,
+int hd_bn_bwd_apply(const void* dout, const void* out, const float* act_scale, const float* act_shift,
+                    const void* y, const float* coef, void* dy, const void* ys,
                     const float* coef_s, void* dys, void* gout, long long npix, int C, hd_stream_t stream);
 int hd_maxpool2_bwd(const void* x, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
                     int W, int C, hd_stream_t stream);

@@ -177,6 +177,7 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const
 // yhat = (y - mean) * rstd.
 template <bool SECOND>
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ ys,
                                      const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
@@ -187,9 +188,14 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
     const int row = threadIdx.x / cvec;             // pixel lane inside the block
     const int rows = blockDim.x / cvec;
     const int c0 = lane_c << 3;
-    float m[8], r[8], ms[8], rs[8];
+    // out == nullptr: the ReLU mask of a plain conv+BN+ReLU is recomputed from y (z > 0 <=> y*scale+shift > 0),
+    // which saves reading the activated tensor
+    const bool remask = out == nullptr;
+    float m[8], r[8], ms[8], rs[8], asc[8], ash[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+        asc[j] = remask ? act_scale[c0 + j] : 0.f;
+        ash[j] = remask ? act_shift[c0 + j] : 0.f;
         m[j] = mean[c0 + j];
         r[j] = rstd[c0 + j];
         ms[j] = SECOND ? mean_s[c0 + j] : 0.f;
@@ -202,9 +208,14 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
          pix += static_cast<size_t>(gridDim.x) * rows) {
         const size_t off = pix * C + c0;
         F8 g = load8(dout + off);
-        F8 o = load8(out + off);
         F8 yy = load8(y + off);
-        F8 y2;
+        F8 o, y2;
+        if (remask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], asc[j], ash[j]);
+        } else {
+            o = load8(out + off);
+        }
         if (SECOND) y2 = load8(ys + off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -264,12 +275,16 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
 // g = dout * (out > 0);  dy = a*g + b*y + c ; optionally dys = as*g + bs*ys + cs ; optionally gout = g
 template <bool SECOND, bool WRITE_G>
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                    const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
                                     const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
                                     __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
-    __shared__ float p[6][256];
+    __shared__ float p[8][256];
+    const bool remask = out == nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        p[6][i] = remask ? act_scale[i] : 0.f;
+        p[7][i] = remask ? act_shift[i] : 0.f;
         p[0][i] = coef[i];
         p[1][i] = coef[C + i];
         p[2][i] = coef[2 * C + i];
@@ -285,9 +300,14 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int c0 = static_cast<int>(i % cvec) << 3;
         F8 g = load8(dout + i * 8);
-        F8 o = load8(out + i * 8);
         F8 yy = load8(y + i * 8);
-        F8 r, r2, y2;
+        F8 o, r, r2, y2;
+        if (remask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], p[6][c0 + j], p[7][c0 + j]);
+        } else {
+            o = load8(out + i * 8);
+        }
         if (SECOND) y2 = load8(ys + i * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -483,19 +503,21 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, cvp y, const float* mean, const float* rstd, cvp ys,
+extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
+                                const float* mean, const float* rstd, cvp ys,
                                 const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
                                 cudaStream_t stream) {
     HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
+    HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_reduce: need `out` or the activation scale/shift");
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     if (ys) {
-        bn_bwd_reduce_kernel<true><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, BF(ys), mean_s,
+        bn_bwd_reduce_kernel<true><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), mean, rstd, BF(ys), mean_s,
                                                                 rstd_s, sums, static_cast<size_t>(npix), C);
     } else {
-        bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), BF(y), mean, rstd, nullptr,
+        bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), mean, rstd, nullptr,
                                                                  nullptr, nullptr, sums, static_cast<size_t>(npix), C);
     }
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
@@ -512,20 +534,21 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, cvp y, const float* coef, void* dy, cvp ys, const float* coef_s,
+extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
+                               const float* coef, void* dy, cvp ys, const float* coef_s,
                                void* dys, void* gout, long long npix, int C, cudaStream_t stream) {
     HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_bwd_apply: C=%d", C);
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
     if (ys && gout)
-        bn_bwd_apply_kernel<true, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C);
+        bn_bwd_apply_kernel<true, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C);
     else if (ys)
-        bn_bwd_apply_kernel<true, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C);
+        bn_bwd_apply_kernel<true, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C);
     else if (gout)
-        bn_bwd_apply_kernel<false, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C);
+        bn_bwd_apply_kernel<false, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C);
     else
-        bn_bwd_apply_kernel<false, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C);
+        bn_bwd_apply_kernel<false, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -96,6 +96,7 @@ struct hd_net {
     void* wgrad_ws = nullptr;
     size_t wgrad_ws_bytes = 0;
     float* small = nullptr;   // scratch for BN-backward sums / coefficients
+    void* pack_jobs_dev = nullptr;          // device copy of the weight-pack job table
     // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
     // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
     Arena wg;
@@ -205,21 +206,48 @@ static void plan_persistent(hd_net* n) {
         }
     }
     n->small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
+    n->pack_jobs_dev = a.alloc(2 * n->units.size() * 64);
     n->persist_bytes = stats_total * sizeof(float);
 }
 
+// Host mirror of hd::PackJob (csrc/pack.cu).
+struct PackJobHost {
+    const float* w;
+    bf16* out;
+    int cout, cin, taps, rows_pad, k_pad, mode;
+    long long start;
+};
+extern "C" int hd_pack_all_weights(const void* jobs, int njobs, long long total, cudaStream_t stream);
+
+// One launch repacks every conv weight (fp32 OIHW master -> bf16 UMMA operands). The job table lives in the
+// persistent arena and is uploaded with every forward (parameters may have moved).
 static void pack_weights(hd_net* n, bool need_dgrad) {
+    std::vector<PackJobHost> jobs;
+    long long total = 0;
     for (size_t i = 0; i < n->units.size(); ++i) {
         Unit& u = n->units[i];
         const hd_unit_ptrs& p = UP(n, static_cast<int>(i));
+        PackJobHost j{};
+        j.w = p.w; j.cout = u.cout; j.cin = u.cin;
         if (u.kind == 1) {
-            RUN(hd_stem_pack_weight(p.w, u.wp, u.cout, n->stream));
+            j.out = u.wp; j.taps = 1; j.rows_pad = 64; j.k_pad = 192; j.mode = 2;
+            j.start = total; total += 64ll * 192; jobs.push_back(j);
             continue;
         }
-        RUN(hd_pack_conv_weight(p.w, u.wp, u.cout, u.cin, u.k, block_n_for(u.cout), pad64(u.cin), 0, n->stream));
-        if (need_dgrad && u.wpd)
-            RUN(hd_pack_conv_weight(p.w, u.wpd, u.cout, u.cin, u.k, block_n_for(u.cin), pad64(u.cout), 1, n->stream));
+        j.taps = u.k * u.k;
+        j.out = u.wp; j.rows_pad = block_n_for(u.cout); j.k_pad = pad64(u.cin); j.mode = 0;
+        j.start = total; total += static_cast<long long>(j.taps) * j.rows_pad * j.k_pad; jobs.push_back(j);
+        if (need_dgrad && u.wpd) {
+            j.out = u.wpd; j.rows_pad = block_n_for(u.cin); j.k_pad = pad64(u.cout); j.mode = 1;
+            j.start = total; total += static_cast<long long>(j.taps) * j.rows_pad * j.k_pad; jobs.push_back(j);
+        }
     }
+    const size_t bytes = jobs.size() * sizeof(PackJobHost);
+    // 3.6 KB pageable -> device copy per forward: stream-ordered, and the host vector may die when the call returns
+    // (the runtime stages pageable sources before returning)
+    if (n->rc == 0 && cudaMemcpyAsync(n->pack_jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice, n->stream) != cudaSuccess)
+        n->rc = fail(HD_ERR_CUDA, "net_forward: upload of the weight-pack table failed");
+    RUN(hd_pack_all_weights(n->pack_jobs_dev, static_cast<int>(jobs.size()), total, n->stream));
 }
 
 // conv (+ bias) -> raw output + BN statistics; then finalize the BN of this unit
@@ -381,8 +409,9 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
     const float* mean = u.bnp + 2 * C;
     const float* rstd = u.bnp + 3 * C;
     const Unit* s = us >= 0 ? &n->units[us] : nullptr;
-    RUN(hd_bn_bwd_reduce(dout, out, y, mean, rstd, ys, s ? s->bnp + 2 * C : nullptr, s ? s->bnp + 3 * C : nullptr, sums,
-                         u.npix, C, n->stream));
+    // out == nullptr: plain conv+BN+ReLU unit, the mask is recomputed from y and this unit's scale/shift
+    RUN(hd_bn_bwd_reduce(dout, out, u.bnp, u.bnp + C, y, mean, rstd, ys, s ? s->bnp + 2 * C : nullptr,
+                         s ? s->bnp + 3 * C : nullptr, sums, u.npix, C, n->stream));
     RUN(hd_bn_bwd_finalize(sums, sums + C, static_cast<float>(u.npix), p.gamma, mean, rstd, coef, p.dgamma, p.dbeta, 0,
                            C, n->stream));
     if (s) {
@@ -390,7 +419,8 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
         RUN(hd_bn_bwd_finalize(sums, sums + 2 * C, static_cast<float>(u.npix), ps.gamma, s->bnp + 2 * C,
                                s->bnp + 3 * C, coef_s, ps.dgamma, ps.dbeta, 0, C, n->stream));
     }
-    RUN(hd_bn_bwd_apply(dout, out, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout, u.npix, C, n->stream));
+    RUN(hd_bn_bwd_apply(dout, out, u.bnp, u.bnp + C, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout, u.npix, C,
+                        n->stream));
 }
 
 static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
@@ -412,7 +442,7 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     cudaEvent_t e2 = mark_ready(n);
     wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W, e2);
     if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W, e2);
-    bn_bwd_unit(n, r.u1, dZ1, r.Z1, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
+    bn_bwd_unit(n, r.u1, dZ1, nullptr, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
     if (r.us < 0) {
         dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
     } else {
@@ -485,7 +515,7 @@ static void backward_impl(hd_net* n, const float* dlogits) {
         bf16* dF1 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         residual_bwd(n, s.neck_res, dF2, dF1, B);
         bf16* dYn = reinterpret_cast<bf16*>(n->bw.alloc(full4));
-        bn_bwd_unit(n, s.u_neck, dF1, s.F1, s.Yn, dYn, -1, nullptr, nullptr, nullptr);
+        bn_bwd_unit(n, s.u_neck, dF1, nullptr, s.Yn, dYn, -1, nullptr, nullptr, nullptr);
         RUN(hd_colsum(dYn, UP(n, s.u_neck).db, npix4, C, C, n->stream));
         bf16* dHg = dF1;  // dead
         dgrad_unit(n, s.u_neck, dYn, dHg, B, H4, W4, nullptr);
@@ -505,7 +535,7 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     residual_bwd(n, n->r_pre1, dR1, dZ0, B);
     bf16* dY0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
-    bn_bwd_unit(n, 0, dZ0, n->Z0, n->Y0, dY0, -1, nullptr, nullptr, nullptr);
+    bn_bwd_unit(n, 0, dZ0, nullptr, n->Y0, dY0, -1, nullptr, nullptr, nullptr);
     cudaEvent_t e0 = mark_ready(n);
     RUN(hd_colsum(dY0, UP(n, 0).db, static_cast<long long>(B) * H2 * W2, 64, 64, n->stream));
     wgrad_unit(n, 0, n->patches, dY0, B, H2, W2, e0);

@@ -54,7 +54,52 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
     y[idx] = __bfloat162float(x[((static_cast<size_t>(n) * H + h) * W + wv) * c_stride + c]);
 }
 
+// All conv weights of a network in ONE launch: `jobs` is a device table, `starts[j]` the first flat output element of
+// job j (ascending), `total` the number of output elements over all jobs.
+struct PackJob {
+    const float* w;
+    __nv_bfloat16* out;
+    int cout, cin, taps, rows_pad, k_pad, mode;   // mode 0 forward, 1 dgrad, 2 stem (K = (ky*7+kx)*3+c, padded)
+    long long start;
+};
+
+__global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int lo = 0, hi = njobs - 1;          // last job with start <= idx
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].start <= idx) lo = mid; else hi = mid - 1;
+    }
+    const PackJob j = jobs[lo];
+    const int e = static_cast<int>(idx - j.start);
+    const int k = e % j.k_pad;
+    const int r = (e / j.k_pad) % j.rows_pad;
+    const int tap = e / (j.k_pad * j.rows_pad);
+    float v = 0.f;
+    if (j.mode == 0) {
+        if (r < j.cout && k < j.cin) v = j.w[(static_cast<size_t>(r) * j.cin + k) * j.taps + tap];
+    } else if (j.mode == 1) {
+        if (r < j.cin && k < j.cout) v = j.w[(static_cast<size_t>(k) * j.cin + r) * j.taps + (j.taps - 1 - tap)];
+    } else {
+        if (r < j.cout && k < 147) v = j.w[(static_cast<size_t>(r) * 3 + (k % 3)) * 49 + (k / 3)];
+    }
+    j.out[e] = __float2bfloat16(v);
+}
+
 }  // namespace hd
+
+// jobs: device array of hd::PackJob (layout documented in csrc/pack.cu); used by the network executor.
+extern "C" int hd_pack_all_weights(const void* jobs, int njobs, long long total, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(njobs > 0 && total > 0, "pack_all_weights: empty job table");
+    const long long blocks = (total + 255) / 256;
+    HD_REQUIRE(blocks < (1ll << 31), "pack_all_weights: too many elements");
+    pack_all_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs), njobs,
+                                                                      total);
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
 
 extern "C" int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int ksize, int rows_pad,
                                    int k_pad, int mode, cudaStream_t stream) {

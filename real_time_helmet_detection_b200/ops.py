@@ -164,13 +164,14 @@ def upsample2_add(up1, low):
     return out
 
 
-def bn_bwd(dout, out, y, bnp, gamma, ys=None, bnp_s=None, gamma_s=None, want_g=False):
+def bn_bwd(dout, out, y, bnp, gamma, ys=None, bnp_s=None, gamma_s=None, want_g=False, remask=False):
     """Backward of relu(bn(y) [+ bn_s(ys) | + x]) w.r.t. y (and ys): returns dy, dys, g, (dgamma, dbeta), (dgamma_s, dbeta_s)."""
     C = y.shape[-1]
     npix = y.numel() // C
     sums = torch.zeros((3, C), dtype=torch.float32, device=y.device)
     L = _lib.lib()
-    check(L.hd_bn_bwd_reduce(ptr(dout), ptr(out), ptr(y), ptr(bnp[2]), ptr(bnp[3]), ptr(ys),
+    out_arg = None if remask else out     # remask: rebuild the ReLU mask from y*scale+shift instead of reading `out`
+    check(L.hd_bn_bwd_reduce(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]), ptr(y), ptr(bnp[2]), ptr(bnp[3]), ptr(ys),
                              ptr(bnp_s[2]) if ys is not None else None, ptr(bnp_s[3]) if ys is not None else None,
                              ptr(sums), npix, C, stream()), "bn_bwd_reduce")
     coef = torch.empty((3, C), dtype=torch.float32, device=y.device)
@@ -189,7 +190,8 @@ def bn_bwd(dout, out, y, bnp, gamma, ys=None, bnp_s=None, gamma_s=None, want_g=F
         dys = torch.empty_like(ys)
     dy = torch.empty_like(y)
     g = torch.empty_like(y) if want_g else None
-    check(L.hd_bn_bwd_apply(ptr(dout), ptr(out), ptr(y), ptr(coef), ptr(dy), ptr(ys), ptr(coef_s), ptr(dys), ptr(g),
+    check(L.hd_bn_bwd_apply(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]), ptr(y), ptr(coef), ptr(dy), ptr(ys),
+                            ptr(coef_s), ptr(dys), ptr(g),
                             npix, C, stream()), "bn_bwd_apply")
     return dy, dys, g, (dgamma, dbeta), (dgs, dbs)
 

@@ -47,3 +47,42 @@ def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, 
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
     return total_loss.detach()
+
+
+class DevicePrefetcher:
+    """Iterates over host batches (tuples of pinned CPU tensors) and yields them on the device, copying batch i+1 on a
+    side stream while batch i is being consumed — the H2D copy of every step still happens, it just overlaps compute.
+
+    Plays the role of `image.to(device)` / `gt.to(device)` in the reference loop (train.py:99,115-118), which copies
+    synchronously (and re-copies the targets once per stack).
+    """
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self.next = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in host)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        batch = self.next
+        for t in batch:
+            if torch.is_tensor(t):
+                t.record_stream(torch.cuda.current_stream(self.device))
+        self._preload()
+        return batch

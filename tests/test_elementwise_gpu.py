@@ -104,6 +104,14 @@ def test_bn_backward(cuda_device, skip_bn):
     assert torch.allclose(db.cpu(), beta.grad, rtol=2e-3, atol=2e-3 * beta.grad.abs().max().item())
     gref = dout * (out.detach() > 0)
     close_bf16(nchw(gout), gref)
+    if not skip_bn:
+        # plain conv+BN+ReLU unit: same result with the ReLU mask recomputed from y instead of read from `out`
+        yb = y.detach()
+        z = F.relu(F.batch_norm(yb, None, None, gamma.detach(), beta.detach(), training=True)).requires_grad_(False)
+        yr = yb.clone().requires_grad_(True)
+        F.relu(F.batch_norm(yr, None, None, gamma.detach(), beta.detach(), training=True)).backward(dout)
+        dy2 = ops.bn_bwd(nhwc(dout, d), None, nhwc(yb, d), bnp, gamma.detach().to(d), remask=True)[0]
+        close_bf16(nchw(dy2), yr.grad, extra=2e-3 * yr.grad.abs().max().item())
     if skip_bn:
         close_bf16(nchw(dys), ys.grad, extra=2e-3 * scale)
         assert torch.allclose(dgs.cpu(), gamma_s.grad, rtol=2e-3, atol=2e-3 * gamma_s.grad.abs().max().item())

@@ -100,12 +100,19 @@ struct hd_net {
     // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
     // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
     Arena wg;
+    // second execution lane: every hourglass level runs its `up1` residual (and that residual's backward) on `alt`
+    // while the spine (pool -> low1 -> ... -> low3) continues on the caller's stream, so that one lane's HBM-bound
+    // BN / ReLU kernels overlap the other lane's tensor-core convolutions. The lane owns a stream, a backward
+    // stack arena and a BN-backward scratch block; `swap_lane` makes it the current one.
+    struct LaneState { cudaStream_t stream = nullptr; Arena bw; float* small = nullptr; } alt;
+    cudaStream_t alt_stream = nullptr;
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> events;
     size_t ev_next = 0;
     ~hd_net() {
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (side) cudaStreamDestroy(side);
+        if (alt_stream) cudaStreamDestroy(alt_stream);
     }
 };
 
@@ -206,6 +213,7 @@ static void plan_persistent(hd_net* n) {
         }
     }
     n->small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
+    n->alt.small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->pack_jobs_dev = a.alloc(2 * n->units.size() * 64);
     n->persist_bytes = stats_total * sizeof(float);
 }
@@ -248,6 +256,38 @@ static void pack_weights(hd_net* n, bool need_dgrad) {
     if (n->rc == 0 && cudaMemcpyAsync(n->pack_jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice, n->stream) != cudaSuccess)
         n->rc = fail(HD_ERR_CUDA, "net_forward: upload of the weight-pack table failed");
     RUN(hd_pack_all_weights(n->pack_jobs_dev, static_cast<int>(jobs.size()), total, n->stream));
+}
+
+static cudaEvent_t next_event(hd_net* n) {
+    if (n->events.empty()) {
+        n->events.resize(128);
+        for (cudaEvent_t& e : n->events)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                n->rc = fail(HD_ERR_CUDA, "net: cudaEventCreate failed");
+                return nullptr;
+            }
+    }
+    return n->events[n->ev_next++ % n->events.size()];
+}
+
+// Event recorded on the CURRENT lane's stream (nullptr in dry mode).
+static cudaEvent_t mark_ready(hd_net* n) {
+    if (n->dry || n->rc != 0) return nullptr;
+    cudaEvent_t e = next_event(n);
+    if (e && cudaEventRecord(e, n->stream) != cudaSuccess) n->rc = fail(HD_ERR_CUDA, "net: cudaEventRecord failed");
+    return e;
+}
+
+static void wait_on(hd_net* n, cudaStream_t waiter, cudaEvent_t e) {
+    if (n->dry || n->rc != 0 || !e) return;
+    if (cudaStreamWaitEvent(waiter, e, 0) != cudaSuccess) n->rc = fail(HD_ERR_CUDA, "net: cudaStreamWaitEvent failed");
+}
+
+// Make the other lane current (stream, backward stack arena, BN-backward scratch).
+static void swap_lane(hd_net* n) {
+    std::swap(n->stream, n->alt.stream);
+    std::swap(n->bw, n->alt.bw);
+    std::swap(n->small, n->alt.small);
 }
 
 // conv (+ bias) -> raw output + BN statistics; then finalize the BN of this unit
@@ -296,7 +336,13 @@ static bf16* hourglass_fwd(hd_net* n, int hi, bf16* x, int B, int H, int W, int 
     HgSaved& h = n->hgs[hi];
     h.x = x; h.H = H; h.W = W;
     const int C = n->in_ch;
+    // up1 on the other lane (it only needs x), the spine on this one; join before the upsample-add
+    cudaEvent_t x_ready = mark_ready(n);
+    swap_lane(n);
+    wait_on(n, n->stream, x_ready);
     bf16* up1 = residual_fwd(n, h.up1, x, B, H, W, training);
+    cudaEvent_t up1_done = mark_ready(n);
+    swap_lane(n);
     bf16* pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H / 2, W / 2, C)));
     RUN(hd_maxpool2(x, pool, B, H, W, C, n->stream));
     bf16* low1 = residual_fwd(n, h.low1, pool, B, H / 2, W / 2, training);
@@ -304,6 +350,7 @@ static bf16* hourglass_fwd(hd_net* n, int hi, bf16* x, int B, int H, int W, int 
                                 : residual_fwd(n, h.low2_res, low1, B, H / 2, W / 2, training);
     bf16* low3 = residual_fwd(n, h.low3, low2, B, H / 2, W / 2, training);
     h.out = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H, W, C)));
+    wait_on(n, n->stream, up1_done);
     RUN(hd_upsample2_add(up1, low3, h.out, B, H, W, C, n->stream));
     return h.out;
 }
@@ -361,28 +408,11 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// Event recorded on the main stream at the point where a wgrad operand (dY) is complete.
-static cudaEvent_t mark_ready(hd_net* n) {
-    if (n->dry || n->rc != 0) return nullptr;
-    if (n->events.empty()) {
-        n->events.resize(96);
-        for (cudaEvent_t& e : n->events)
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-                n->rc = fail(HD_ERR_CUDA, "net_backward: cudaEventCreate failed");
-                return nullptr;
-            }
-    }
-    cudaEvent_t e = n->events[n->ev_next++ % n->events.size()];
-    if (cudaEventRecord(e, n->stream) != cudaSuccess) n->rc = fail(HD_ERR_CUDA, "net_backward: cudaEventRecord failed");
-    return e;
-}
-
 // Weight gradient on the side stream, ordered after `ready` (the dY producer) of the main stream.
 static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, int H, int W, cudaEvent_t ready) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
-    if (!n->dry && n->rc == 0 && ready && cudaStreamWaitEvent(n->side, ready, 0) != cudaSuccess)
-        n->rc = fail(HD_ERR_CUDA, "net_backward: cudaStreamWaitEvent failed");
+    wait_on(n, n->side, ready);
     if (u.kind == 1)
         RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->side));
     else
@@ -460,6 +490,14 @@ static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const b
     const int H = h.H, W = h.W, C = n->in_ch;
     const size_t mark = n->bw.off;
     const size_t half = act_bytes(B, H / 2, W / 2, C), full = act_bytes(B, H, W, C);
+    // up1's backward (needs only dOut) on the other lane; its result d_xa is consumed by this lane's max-pool backward
+    bf16* d_xa = reinterpret_cast<bf16*>(n->bw.alloc(full));
+    cudaEvent_t dout_ready = mark_ready(n);
+    swap_lane(n);
+    wait_on(n, n->stream, dout_ready);
+    residual_bwd(n, h.up1, dOut, d_xa, B);
+    cudaEvent_t up1_done = mark_ready(n);
+    swap_lane(n);
     bf16* d_low3 = reinterpret_cast<bf16*>(n->bw.alloc(half));
     RUN(hd_sum2x2(dOut, d_low3, B, H, W, C, n->stream));
     bf16* d_low2 = reinterpret_cast<bf16*>(n->bw.alloc(half));
@@ -467,10 +505,9 @@ static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const b
     bf16* d_low1 = d_low3;  // d_low3 is dead
     if (h.low2_hg >= 0) hourglass_bwd(n, h.low2_hg, d_low2, d_low1, nullptr, B);
     else residual_bwd(n, h.low2_res, d_low2, d_low1, B);
-    bf16* d_pool = d_low2;  // dead as well
+    bf16* d_pool = d_low2;  // dead as well (a nested level has joined its up1 lane before returning)
     residual_bwd(n, h.low1, d_low1, d_pool, B);
-    bf16* d_xa = reinterpret_cast<bf16*>(n->bw.alloc(full));
-    residual_bwd(n, h.up1, dOut, d_xa, B);
+    wait_on(n, n->stream, up1_done);
     RUN(hd_maxpool2_bwd(h.x, d_pool, d_xa, extra_add, dX, B, H, W, C, n->stream));
     n->bw.off = mark;
 }
@@ -541,8 +578,8 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     wgrad_unit(n, 0, n->patches, dY0, B, H2, W2, e0);
     // join: everything the side stream produced (all weight gradients) is ordered before whatever follows on `stream`
     if (!n->dry && n->rc == 0) {
-        cudaEvent_t done = n->events[n->ev_next++ % n->events.size()];
-        if (cudaEventRecord(done, n->side) != cudaSuccess || cudaStreamWaitEvent(n->stream, done, 0) != cudaSuccess)
+        cudaEvent_t done = next_event(n);
+        if (!done || cudaEventRecord(done, n->side) != cudaSuccess || cudaStreamWaitEvent(n->stream, done, 0) != cudaSuccess)
             n->rc = fail(HD_ERR_CUDA, "net_backward: stream join failed");
     }
 }
@@ -584,9 +621,11 @@ extern "C" size_t hd_net_workspace_bytes(hd_net* n, int B, int H, int W, int wit
     size_t total = head + ((n->fw.peak + 255) & ~size_t(255));
     if (with_backward) {
         n->bw = Arena();
+        n->alt.bw = Arena();
         n->wg = Arena();
         backward_impl(n, nullptr);
-        total += ((n->bw.peak + 255) & ~size_t(255)) + ((n->wg.peak + 255) & ~size_t(255));
+        total += ((n->bw.peak + 255) & ~size_t(255)) + ((n->alt.bw.peak + 255) & ~size_t(255)) +
+                 ((n->wg.peak + 255) & ~size_t(255));
     }
     n->dry = false;
     n->trained_fwd = false;
@@ -604,6 +643,10 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
     HD_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "net_forward: workspace must be 256-byte aligned");
     size_t head = 0;
     n->dry = false; n->rc = 0; n->up = units; n->stream = stream;
+    if (!n->alt_stream && cudaStreamCreateWithFlags(&n->alt_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(HD_ERR_CUDA, "net_forward: cannot create the second lane's stream");
+    static const bool single_lane = getenv("HD_SINGLE_LANE") != nullptr;   // debug knob: everything on one stream
+    n->alt.stream = single_lane ? stream : n->alt_stream;
     plan(n, reinterpret_cast<uint8_t*>(workspace), workspace_bytes, B, H, W, training != 0, &head);
     n->B = B; n->H = H; n->W = W;
     // capacity check with a dry pass first (cheap: pointer arithmetic only)
@@ -638,18 +681,25 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     static const bool serial = getenv("HD_SERIAL_WGRAD") != nullptr;   // debug knob: wgrad on the main stream
     cudaStream_t side_keep = n->side;
     if (serial) n->side = stream;
-    // capacity check (dry) then run: [wg: bump-only dY operands][bw: stack-allocated temporaries]
+    if (!n->alt_stream && cudaStreamCreateWithFlags(&n->alt_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(HD_ERR_CUDA, "net_backward: cannot create the second lane's stream");
+    static const bool single_lane = getenv("HD_SINGLE_LANE") != nullptr;
+    n->alt.stream = single_lane ? stream : n->alt_stream;
+    // capacity check (dry) then run: [wg: bump-only dY operands][bw: this lane's stack][alt.bw: the up1 lane's stack]
     uint8_t* region = n->wg.base;
     const size_t region_cap = n->wg.cap;
     n->dry = true;
-    n->wg = Arena(); n->bw = Arena();
+    n->wg = Arena(); n->bw = Arena(); n->alt.bw = Arena();
     backward_impl(n, nullptr);
-    const size_t wg_need = (n->wg.peak + 255) & ~size_t(255), bw_need = n->bw.peak;
+    const size_t wg_need = (n->wg.peak + 255) & ~size_t(255), bw_need = (n->bw.peak + 255) & ~size_t(255),
+                 alt_need = n->alt.bw.peak;
     n->dry = false;
     n->wg = Arena(); n->wg.base = region; n->wg.cap = region_cap;
-    n->bw = Arena(); n->bw.base = region + wg_need; n->bw.cap = region_cap > wg_need ? region_cap - wg_need : 0;
-    HD_REQUIRE(wg_need + bw_need <= region_cap, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)",
-               region_cap, wg_need + bw_need);
+    n->bw = Arena(); n->bw.base = region + wg_need; n->bw.cap = bw_need;
+    n->alt.bw = Arena(); n->alt.bw.base = region + wg_need + bw_need; n->alt.bw.cap = alt_need;
+    HD_REQUIRE(wg_need + bw_need + alt_need <= region_cap,
+               "net_backward: workspace too small for the backward pass (%zu < %zu bytes)", region_cap,
+               wg_need + bw_need + alt_need);
     backward_impl(n, dlogits);
     n->side = side_keep;
     n->trained_fwd = false;

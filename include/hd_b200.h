@@ -52,6 +52,9 @@ int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, 
 /* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the
  * halo-reuse M=256 kernel (3x3, block_n 128, map >= 16x16) whenever the shape is eligible. */
 void hd_set_conv_variant(int variant);
+/* Profiling only (results are wrong when non-zero): 1 = epilogue drains TMEM but skips math/stores, 2 = MMA issue
+ * skipped, 3 = weight tiles loaded only for a CTA's first tile (halo kernel). */
+void hd_set_conv_debug(int mode);
 
 /* Weight gradient of the same convs (autograd of hourglass.py:100): grad_w (OIHW fp32 [cout][cin_real][k][k])
  * = (accumulate ? grad_w : 0) + sum_pixels dy[p, co] * x[p + tap, ci].  x nhwc [.., cin], dy nhwc [.., cout],

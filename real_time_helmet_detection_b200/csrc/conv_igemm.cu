@@ -46,6 +46,8 @@ struct ConvParams {
     const __nv_bfloat16* addend;  // optional NHWC bf16, same shape as out (mode 0)
     float* stat_sum;          // optional [cout] : sum over pixels of the fp32 conv output (bias included)
     float* stat_sqsum;        // optional [cout]
+    int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
+                              // 2 = MMA issue skipped, 3 = weight tiles loaded only for the first tile
 };
 
 // Sum v[0..31] across the 32 lanes of the warp; on return lane l holds the total of element l.
@@ -65,9 +67,12 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
 
 // Epilogue of one 128-row accumulator block: TMEM -> registers (32 columns at a time) -> bias / residual addend ->
 // bf16 NHWC store, plus the per-channel sum / sum-of-squares (train-mode BN statistics) into s_stat.
+// Stores go through a 2 KB per-warp staging buffer: a lane owns one pixel row, so writing its 64 bytes (32 channels)
+// directly would make every store instruction touch 32 different 128-byte lines with 16 bytes each (measured: the
+// epilogue alone took 78 us of a 123 us kernel). Staged, one instruction writes 8 rows x 64 contiguous bytes.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t taddr, bool valid, size_t pix, uint32_t lane,
-                                              float* s_stat, bool do_stats) {
+                                              float* s_stat, bool do_stats, uint8_t* stage) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
@@ -94,8 +99,8 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
                 }
             }
         }
-        if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0);
+        {
+            const uint32_t swz = (lane >> 1) & 3u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint4 u;
@@ -103,8 +108,20 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
                 u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
                 u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
                 u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                op[q] = u;
+                *reinterpret_cast<uint4*>(stage + lane * 64 + ((static_cast<uint32_t>(q) ^ swz) << 4)) = u;
             }
+            __syncwarp();
+            const uint32_t q = lane & 3u;
+#pragma unroll
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                const uint32_t r = 8u * sidx + (lane >> 2);
+                const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((q ^ ((r >> 1) & 3u)) << 4));
+                const unsigned long long rp = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), r);
+                const int rv = __shfl_sync(0xffffffffu, static_cast<int>(valid), r);
+                if (rv)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + rp * p.out_cs + c0 + q * 8) = w;
+            }
+            __syncwarp();
         }
         if (do_stats) {
             float sq[32];
@@ -139,6 +156,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint64_t* tmem_empty = bars + 2 * kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BLOCK_N]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [4 epilogue warps][2 KB]
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -242,7 +260,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (BLOCK_N >= 32) {
-                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats);
+                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
             } else {
                 // BLOCK_N == 16: prediction head (hourglass.py:189-195), fp32 NCHW logits
                 uint32_t r[16];
@@ -306,7 +324,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kStages * (kABytes + BLOCK_N * 128) + 1024 /*align*/ + 256 /*barriers*/ +
-                               2 * BLOCK_N * 4;
+                               2 * BLOCK_N * 4 + 4 * 2048 /*store staging*/;
     static bool attr_set = false;
     if (!attr_set) {
         HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -330,9 +348,14 @@ constexpr int kHARows = 18 * 16;
 constexpr int kHABytes = kHARows * 128;   // 36,864
 constexpr int kHAStages = 3;
 constexpr int kHBBytes = 128 * 128;       // one (tap, 64-channel chunk) weight tile for 128 output channels
-constexpr int kHBStages = 6;
+constexpr int kHBStages = 5;
 
-__global__ void __launch_bounds__(kThreads, 1)
+// 12 warps: producer, MMA issuer, TMEM allocator, (idle), and EIGHT epilogue warps - warps 4-7 drain accumulator half 0,
+// warps 8-11 half 1 (a warp may only touch the TMEM lane quarter warp_idx % 4). With four warps the BN-statistics
+// epilogue (62 shuffles per 32 columns) was the pacing stage: 148 us with statistics vs 119 us without.
+constexpr int kHaloThreads = 384;
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const ConvParams p) {
     constexpr int BLOCK_N = 128;
@@ -350,6 +373,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [8 epilogue warps][2 KB]
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -360,7 +384,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < kHAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kHBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -385,6 +409,11 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         tma_load_4d(smem_a + sa * kHABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - 1, y0 - 1, n);
                         for (int dy = 0; dy < 3; ++dy) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
+                            if (p.dbg == 3 && tile != static_cast<int>(blockIdx.x)) {
+                                mbar_arrive(&b_full[sb]);
+                                if (++sb == kHBStages) { sb = 0; pb ^= 1; }
+                                continue;
+                            }
                             mbar_arrive_expect_tx(&b_full[sb], kHBBytes);
                             tma_load_3d(smem_b + sb * kHBBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * 3 + dx);
                             if (++sb == kHBStages) { sb = 0; pb ^= 1; }
@@ -417,8 +446,9 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                                 const uint64_t adesc = umma_smem_desc_sw128(a_addr + (dy + 8 * h) * 2048, 0, 1024);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma_bf16(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, kIdesc,
-                                              (first && k == 0) ? 0u : 1u);
+                                    if (p.dbg != 2)
+                                        umma_bf16(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                                                  (first && k == 0) ? 0u : 1u);
                             }
                             umma_commit(&b_empty[sb]);
                         }
@@ -446,20 +476,20 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const int n = tile / (p.tiles_x * p.tiles_y);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            {
+                const int h = (warp - 4) >> 2;            // accumulator half this warp drains
                 const int x = tx * 16 + (row & 15);
                 const int y = ty * 16 + 8 * h + (row >> 4);
                 const bool valid = (x < p.W) && (y < p.H);
                 const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * 128;
-                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats);
+                if (p.dbg != 1) epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
         if (do_stats) {
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             const int t = threadIdx.x - 128;
             if (t < p.cout) {
                 atomicAdd(p.stat_sum + t, s_stat[t]);
@@ -473,10 +503,188 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-static int g_conv_variant = 0;  // 0 auto, 1 always generic, 2 halo whenever the shape allows (tests)
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) of the halo kernel. The halo kernel is limited by the shared-memory operand port:
+// an SS-mode M=128 N=128 K=16 MMA re-reads 4 KB of A and 4 KB of B per 64 cycles (= the 128 B/clk port), and the TMA
+// fill traffic shares that port. Here two CTAs of a cluster cooperate on one 16x16-pixel tile (M = 256):
+//   * each CTA owns 8 tile rows: its activation box is 10 rows x 16 columns per dx (20 KB instead of 36 KB);
+//   * each CTA holds HALF of the output channels of ALL 9 x chunks weight tiles, loaded once and kept resident
+//     (147 KB for cin = 128) - weights are never re-streamed and each SM reads only N/2 rows of B per MMA;
+//   * the leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M=256, N=128); accumulators live in both CTAs' TMEM;
+//   * TMA completions of both CTAs are signalled on the leader's mbarriers, tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" arrivals to both CTAs, epilogue warps of both CTAs release the accumulator
+//     on the leader's barrier.
+constexpr int kPARows = 10 * 16;
+constexpr int kPABytes = kPARows * 128;   // 20,480
+constexpr int kPAStages = 3;
+constexpr int kPBTile = 64 * 128;         // one (tap, chunk) half-tile: 64 output channels x 64 k
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w64,
+                       const ConvParams p) {
+    constexpr int BLOCK_N = 128;
+    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0, 256);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_tiles = 9 * p.cin_chunks;
+    uint8_t* smem_b = smem;                               // resident weights: b_tiles x 8 KB
+    uint8_t* smem_a = smem + 18 * kPBTile;                // activation ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kPAStages * kPABytes);
+    uint64_t* a_full = bars;                              // leader's are used (count 2: one arrive per CTA + tx bytes)
+    uint64_t* a_empty = a_full + kPAStages;               // local, arrived by the multicast commit
+    uint64_t* b_full = a_empty + kPAStages;               // leader's is used
+    uint64_t* tmem_full = b_full + 1;                     // local, multicast commit
+    uint64_t* tmem_empty = tmem_full + 2;                 // leader's are used (count 2 x 128)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [4 epilogue warps][2 KB]
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w64);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < kPAStages; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+        mbar_init(b_full, 2);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        fence_mbar_init();
+    }
+    if (threadIdx.x < 2 * BLOCK_N) s_stat[threadIdx.x] = 0.f;
+    cluster_sync();                                       // barriers of both CTAs initialised before any remote use
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // resident weights: this CTA's 64 output channels of every (tap, chunk) tile
+            const uint32_t bfull0 = mapa_u32(smem_u32(b_full), 0);
+            if (leader) mbar_arrive_expect_tx(b_full, 2u * b_tiles * kPBTile);
+            else mbar_arrive_cluster(bfull0);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int ck = 0; ck < p.cin_chunks; ++ck)
+                    tma_load_3d_2sm(smem_b + (tap * p.cin_chunks + ck) * kPBTile, &tmap_w64, bfull0, ck * 64,
+                                    64 * static_cast<int>(rank), tap);
+            uint32_t sa = 0, pa = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int n = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * 16, y0 = ty * 16 + 8 * static_cast<int>(rank);
+                for (int dx = 0; dx < 3; ++dx) {
+                    for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                        mbar_wait(&a_empty[sa], pa ^ 1);
+                        const uint32_t afull0 = mapa_u32(smem_u32(&a_full[sa]), 0);
+                        if (leader) mbar_arrive_expect_tx(&a_full[sa], 2u * kPABytes);
+                        else mbar_arrive_cluster(afull0);
+                        tma_load_4d_2sm(smem_a + sa * kPABytes, &tmap_x, afull0, ck * 64, x0 + dx - 1, y0 - 1, n);
+                        if (++sa == kPAStages) { sa = 0; pa ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        uint32_t sa = 0, pa = 0, it = 0;
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 128;
+            bool first = true;
+            for (int dx = 0; dx < 3; ++dx) {
+                for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem_a + sa * kPABytes);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t adesc = umma_smem_desc_sw128(a_addr + dy * 2048, 0, 1024);
+                            const uint64_t bdesc = umma_smem_desc_sw128(
+                                smem_u32(smem_b + ((dy * 3 + dx) * p.cin_chunks + ck) * kPBTile), 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                                              (first && dy == 0 && k == 0) ? 0u : 1u);
+                        }
+                        umma_commit_2sm(&a_empty[sa], 3);
+                    }
+                    __syncwarp();
+                    first = false;
+                    if (++sa == kPAStages) { sa = 0; pa ^= 1; }
+                }
+            }
+            if (elect_one()) umma_commit_2sm(&tmem_full[acc], 3);
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        const int row = ew * 32 + (int)lane;
+        const bool do_stats = p.stat_sum != nullptr;
+        uint32_t it = 0;
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int n = tile / (p.tiles_x * p.tiles_y);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int x = tx * 16 + (row & 15);
+            const int y = ty * 16 + 8 * static_cast<int>(rank) + (row >> 4);
+            const bool valid = (x < p.W) && (y < p.H);
+            const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 128;
+            epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (do_stats) {
+            named_bar_sync(1, 128);
+            const int t = threadIdx.x - 128;
+            if (t < p.cout) {
+                atomicAdd(p.stat_sum + t, s_stat[t]);
+                atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                                       // nobody exits while the peer may still signal its barriers
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
+}
+
+static int g_conv_debug = 0;
+static bool g_pair_default = false;   // the CTA-pair kernel is correct but measured slower than the halo kernel (profiles/README.md)
+static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible, 3 CTA-pair whenever eligible
+
+static int launch_conv_pair(const CUtensorMap& tx, const CUtensorMap& tw64, const ConvParams& p, cudaStream_t stream) {
+    constexpr int smem_bytes = 18 * kPBTile + kPAStages * kPABytes + 1024 + 256 + 2 * 128 * 4 + 4 * 2048;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        attr_set = true;
+    }
+    int clusters = sm_count() / 2;
+    if (p.num_tiles < clusters) clusters = p.num_tiles;
+    conv_igemm_pair_kernel<<<2 * clusters, kThreads, smem_bytes, stream>>>(tx, tw64, p);
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
 
 static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-    constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4;
+    constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 8 * 2048;
     static bool attr_set = false;
     if (!attr_set) {
         HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -484,7 +692,7 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_igemm_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tx, tw, p);
+    conv_igemm_halo_kernel<<<grid, kHaloThreads, smem_bytes, stream>>>(tx, tw, p);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -493,6 +701,8 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
 
 // Test / tuning knob: 0 auto, 1 generic kernel only, 2 halo kernel whenever the shape is eligible.
 extern "C" void hd_set_conv_variant(int v) { hd::g_conv_variant = v; }
+// Profiling only: see ConvParams::dbg (results are wrong when non-zero).
+extern "C" void hd_set_conv_debug(int v) { hd::g_conv_debug = v; }
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
@@ -526,14 +736,16 @@ extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, v
     p.out = out; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_cs = out2_cs;
     p.bias = bias; p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
     p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
+    p.dbg = g_conv_debug;
 
     // halo variant: 3x3, 128 output channels, map >= 16x16 and enough 16x16 tiles to fill the machine
-    bool halo = false;
+    bool halo = false, pair = false;
     if (ksize == 3 && block_n == 128 && H >= 16 && W >= 16 && out_mode == 0 && g_conv_variant != 1) {
         const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
-        halo = g_conv_variant == 2 || ht >= sm_count();
-        if (halo) {
-            tw = 16; th = 18; tn = 1;
+        pair = g_conv_variant == 3 || (g_conv_variant == 0 && g_pair_default && ht >= sm_count());
+        halo = !pair && (g_conv_variant == 2 || ht >= sm_count());
+        if (halo || pair) {
+            tw = 16; th = pair ? 10 : 18; tn = 1;
             p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
             p.num_tiles = ht;
         }
@@ -552,6 +764,15 @@ extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, v
         uint32_t box[3] = {64, (uint32_t)block_n, 1};
         int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);
         if (rc) return rc;
+    }
+    if (pair) {
+        alignas(64) CUtensorMap tmw64;
+        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)block_n, (uint64_t)(ksize * ksize)};
+        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)block_n * cin * 2};
+        uint32_t box[3] = {64, 64, 1};
+        int rc = make_tmap_bf16(&tmw64, w_packed, 3, dims, str, box);
+        if (rc) return rc;
+        return launch_conv_pair(tmx, tmw64, p, stream);
     }
     if (halo) return launch_conv_halo(tmx, tmw, p, stream);
     if (block_n == 128) return launch_conv<128>(tmx, tmw, p, stream);

@@ -125,10 +125,11 @@ HALO_CASES = [(2, 32, 32, 128, 128, 3), (1, 64, 48, 128, 128, 3), (1, 40, 24, 12
               (3, 17, 33, 128, 128, 3)]
 
 
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("N,H,W,cin,cout,k", HALO_CASES)
-def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k):
-    """The halo-reuse M=256 kernel (forced) must agree with PyTorch exactly like the generic kernel: forward with bias,
-    residual addend and BN statistics, and dgrad."""
+def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k, variant):
+    """The halo-reuse M=256 kernel (variant 2) and its CTA-pair / cta_group::2 version (variant 3), forced, must agree
+    with PyTorch exactly like the generic kernel: forward with bias, residual addend and BN statistics, and dgrad."""
     from real_time_helmet_detection_b200 import ops, _lib
     g = torch.Generator().manual_seed(77 + H + W)
     x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
@@ -137,7 +138,7 @@ def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k):
     bias = torch.randn(cout, generator=g)
     conv = F.conv2d(x, w, bias, padding=1)
     ref = conv + r
-    _lib.lib().hd_set_conv_variant(2)
+    _lib.lib().hd_set_conv_variant(variant)
     try:
         stats = torch.zeros(2, cout, device=cuda_device)
         y = ops.conv2d_igemm(ops.to_nhwc(x.to(cuda_device)), ops.pack_weight(w.to(cuda_device)), cout, k,

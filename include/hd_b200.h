@@ -98,7 +98,8 @@ int hd_maxpool2(const void* x, void* y, int N, int H, int W, int C, hd_stream_t 
 int hd_upsample2_add(const void* up1, const void* low, void* out, int N, int H, int W, int C,
                      hd_stream_t stream);                                                         /* :147,:156 */
 /* backward counterparts */
-/* g = dout * relu_mask; mask = (out > 0), or, when out == NULL, (y*act_scale + act_shift > 0) recomputed from y. */
+/* g = dout * relu_mask; mask = (out > 0), or, when out == NULL, (y*act_scale + act_shift > 0) recomputed from y.
+ * sums[0] += sum g, sums[1] += sum g*y, sums[2] += sum g*ys (RAW moments; hd_bn_bwd_finalize applies mean / rstd). */
 int hd_bn_bwd_reduce(const void* dout, const void* out, const float* act_scale, const float* act_shift,
                      const void* y, const float* mean, const float* rstd,
                      const void* ys, const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,

@@ -85,19 +85,33 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
         }
-        if (p.addend && valid) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.out_cs + c0);
+        if (p.addend) {
+            // coalesced read of the 32 rows x 64 B addend tile through the staging buffer (8 rows x 64 B per
+            // instruction), then every lane picks up its own row
+            const uint32_t q = lane & 3u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 u = __ldg(ap + q);
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                const uint32_t r = 8u * sidx + (lane >> 2);
+                const unsigned long long rp = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), r);
+                const int rv = __shfl_sync(0xffffffffu, static_cast<int>(valid), r);
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (rv) w = __ldg(reinterpret_cast<const uint4*>(p.addend + rp * p.out_cs + c0 + q * 8));
+                *reinterpret_cast<uint4*>(stage + r * 64 + ((q ^ ((r >> 1) & 3u)) << 4)) = w;
+            }
+            __syncwarp();
+            const uint32_t swz_a = (lane >> 1) & 3u;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((static_cast<uint32_t>(qq) ^ swz_a) << 4));
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float2 f = __bfloat1622float2(h[j]);
-                    v[q * 8 + 2 * j] += f.x;
-                    v[q * 8 + 2 * j + 1] += f.y;
+                    v[qq * 8 + 2 * j] += f.x;
+                    v[qq * 8 + 2 * j + 1] += f.y;
                 }
             }
+            __syncwarp();
         }
         {
             const uint32_t swz = (lane >> 1) & 3u;

@@ -182,19 +182,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         const int row = ew * 32 + (int)lane;  // cout
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        // Each lane owns one cout row of the accumulator; rows are 4*BLOCK_N bytes apart in the workspace, so the
+        // 32x32 fp32 block is transposed through a 4 KB per-warp staging buffer (the dead dY buffer 0 region is not
+        // reusable: other CTAs' pipelines are independent, so a dedicated region after the barriers is used) and
+        // written as 4 rows x 128 contiguous bytes per instruction.
+        float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot) + 16 + 15) & ~uintptr_t(15)) + ew * 1024;
         for (int t = 0; t < p.taps_per_group; ++t) {
             const int tap = HALO ? t * p.kw + group : group * p.taps_per_group + t;
-            float* dst = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * 128 + row) * BLOCK_N;
+            float* dst0 = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * 128 + ew * 32) * BLOCK_N;
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + t * BLOCK_N + c0, r);
                 tmem_ld_wait();
-                float4* d4 = reinterpret_cast<float4*>(dst + c0);
+                // stage[row = lane][32 floats], 16-byte pieces XOR-swizzled by the row
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    d4[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    *reinterpret_cast<float4*>(stage + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                __syncwarp();
+                const int q = lane & 7;
+#pragma unroll
+                for (int sidx = 0; sidx < 8; ++sidx) {
+                    const int rr = 4 * sidx + (lane >> 3);
+                    const float4 w = *reinterpret_cast<const float4*>(stage + rr * 32 + ((q ^ (rr & 7)) << 2));
+                    *reinterpret_cast<float4*>(dst0 + static_cast<size_t>(rr) * BLOCK_N + c0 + q * 4) = w;
+                }
+                __syncwarp();
             }
         }
     }
@@ -230,7 +245,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 template <int BLOCK_N, bool HALO>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
     constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
-    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HALO ? 160 : 128) * BLOCK_N * 2 + 1024 + 256;
+    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HALO ? 160 : 128) * BLOCK_N * 2 + 1024 + 256 + 4 * 4096;
     static bool attr_set = false;
     if (!attr_set) {
         HD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, HALO>,

@@ -36,6 +36,15 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// 8 consecutive per-channel constants from shared memory with two 128-bit loads (the per-element scalar loads of an
+// earlier version made these kernels LDS-issue bound instead of HBM bound)
+__device__ __forceinline__ void lds8(const float* s, int c0, float (&o)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(s + c0);
+    const float4 b = *reinterpret_cast<const float4*>(s + c0 + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 static inline int grid_for(size_t work, int block, int max_blocks) {
     size_t g = (work + block - 1) / block;
     if (g > (size_t)max_blocks) g = max_blocks;
@@ -80,20 +89,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 template <bool RELU>
 __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                               const float* __restrict__ shift, __nv_bfloat16* __restrict__ z, size_t nvec, int C) {
-    __shared__ float s_sc[256], s_sh[256];
+    __shared__ __align__(16) float s_sc[256], s_sh[256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         s_sc[i] = scale[i];
         s_sh[i] = shift[i];
     }
     __syncthreads();
-    const int cvec = C >> 3;
+    // blockDim (256) is a multiple of C/8, so a thread always works on the same 8 channels
+    const int c0 = static_cast<int>(threadIdx.x % (C >> 3)) << 3;
+    float sc[8], sh[8];
+    lds8(s_sc, c0, sc);
+    lds8(s_sh, c0, sh);
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cvec) << 3;
         F8 a = load8(y + i * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float t = fmaf(a.v[j], s_sc[c0 + j], s_sh[c0 + j]);
+            float t = fmaf(a.v[j], sc[j], sh[j]);
             a.v[j] = RELU ? fmaxf(t, 0.f) : t;
         }
         store8(z + i * 8, a);
@@ -106,7 +118,7 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
                                    const float* __restrict__ b2, const __nv_bfloat16* __restrict__ skip,
                                    const float* __restrict__ ss, const float* __restrict__ bs,
                                    __nv_bfloat16* __restrict__ out, size_t nvec, int C) {
-    __shared__ float p[4][256];
+    __shared__ __align__(16) float p[4][256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         p[0][i] = s2[i];
         p[1][i] = b2[i];
@@ -114,17 +126,21 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
         p[3][i] = SKIP_BN ? bs[i] : 0.f;
     }
     __syncthreads();
-    const int cvec = C >> 3;
+    const int c0 = static_cast<int>(threadIdx.x % (C >> 3)) << 3;
+    float k0[8], k1[8], k2[8], k3[8];
+    lds8(p[0], c0, k0);
+    lds8(p[1], c0, k1);
+    lds8(p[2], c0, k2);
+    lds8(p[3], c0, k3);
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cvec) << 3;
         F8 a = load8(y2 + i * 8);
         F8 k = load8(skip + i * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float t = fmaf(a.v[j], p[0][c0 + j], p[1][c0 + j]);
-            float s = SKIP_BN ? fmaf(k.v[j], p[2][c0 + j], p[3][c0 + j]) : k.v[j];
-            a.v[j] = fmaxf(t + s, 0.f);
+            float t = fmaf(a.v[j], k0[j], k1[j]);
+            float sv = SKIP_BN ? fmaf(k.v[j], k2[j], k3[j]) : k.v[j];
+            a.v[j] = fmaxf(t + sv, 0.f);
         }
         store8(out + i * 8, a);
     }
@@ -172,35 +188,31 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-// Per-channel reductions for BN backward behind a ReLU:  g = dout * (out > 0)
-//   sums[0][c] += sum g ; sums[1][c] += sum g * yhat(y) ; sums[2][c] += sum g * yhat(ys)   (ys optional)
-// yhat = (y - mean) * rstd.
-template <bool SECOND>
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
-                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ ys,
-                                     const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
-                                     float* __restrict__ sums, size_t npix, int C) {
-    extern __shared__ float red[];  // [3][C]
+// Per-channel reductions for BN backward behind a ReLU:  g = dout * mask
+//   sums[0][c] += sum g ; sums[1][c] += sum g * y ; sums[2][c] += sum g * ys   (ys optional)   -- RAW moments; the
+// finalize kernel turns them into sum g * yhat = rstd * (sum g*y - mean * sum g). Keeping mean / rstd out of the
+// streaming loop leaves it with no per-channel constants at all (mask from `out`) or just scale/shift (REMASK:
+// the ReLU mask of a plain conv+BN+ReLU is recomputed as y*scale+shift > 0, which saves reading the activated tensor),
+// so the kernel stays at ~50 registers and runs at HBM speed.
+template <bool SECOND, bool REMASK>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
+                     float* __restrict__ sums, size_t npix, int C) {
+    extern __shared__ __align__(16) float red[];  // [3][C]
     const int cvec = C >> 3;
     const int lane_c = threadIdx.x % cvec;          // which 8-channel vector
     const int row = threadIdx.x / cvec;             // pixel lane inside the block
     const int rows = blockDim.x / cvec;
     const int c0 = lane_c << 3;
-    // out == nullptr: the ReLU mask of a plain conv+BN+ReLU is recomputed from y (z > 0 <=> y*scale+shift > 0),
-    // which saves reading the activated tensor
-    const bool remask = out == nullptr;
-    float m[8], r[8], ms[8], rs[8], asc[8], ash[8];
+    float asc[8], ash[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        asc[j] = remask ? act_scale[c0 + j] : 0.f;
-        ash[j] = remask ? act_shift[c0 + j] : 0.f;
-        m[j] = mean[c0 + j];
-        r[j] = rstd[c0 + j];
-        ms[j] = SECOND ? mean_s[c0 + j] : 0.f;
-        rs[j] = SECOND ? rstd_s[c0 + j] : 0.f;
+        asc[j] = REMASK ? act_scale[c0 + j] : 0.f;
+        ash[j] = REMASK ? act_shift[c0 + j] : 0.f;
     }
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
     float a0[8], a1[8], a2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = a2[j] = 0.f;
@@ -210,32 +222,27 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
         F8 g = load8(dout + off);
         F8 yy = load8(y + off);
         F8 o, y2;
-        if (remask) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], asc[j], ash[j]);
-        } else {
-            o = load8(out + off);
-        }
+        if (!REMASK) o = load8(out + off);
         if (SECOND) y2 = load8(ys + off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
+            const float pre = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) : o.v[j];
+            const float gj = pre > 0.f ? g.v[j] : 0.f;
             a0[j] += gj;
-            a1[j] += gj * ((yy.v[j] - m[j]) * r[j]);
-            if (SECOND) a2[j] += gj * ((y2.v[j] - ms[j]) * rs[j]);
+            a1[j] = fmaf(gj, yy.v[j], a1[j]);
+            if (SECOND) a2[j] = fmaf(gj, y2.v[j], a2[j]);
         }
     }
-    // block reduction with a tiny shared footprint (3*C floats) so that several of these CTAs can share an SM with a
-    // persistent tcgen05 conv CTA (~194 KB of shared memory) when the executor overlaps them on two streams
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
+    // block reduction with a tiny shared footprint (3*C floats) so that several of these CTAs can share an SM with a
+    // persistent tcgen05 conv CTA when the executor overlaps them on two streams.
     // lanes l and l^16 (cvec == 16) or l^8, l^16 (cvec == 8) hold the same channels of different pixel rows
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        for (int o = cvec; o < 32; o <<= 1) {
-            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
-            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
-            if (SECOND) a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o);
+        for (int o2 = cvec; o2 < 32; o2 <<= 1) {
+            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o2);
+            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o2);
+            if (SECOND) a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o2);
         }
     }
     if ((threadIdx.x & 31) < cvec) {
@@ -256,6 +263,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
 
 // From the reduction sums build the per-channel affine form of the BN input gradient
 //   dy = a * g + b * y + c      with  a = gamma*rstd, b = -gamma*rstd^2*S1/M, c = gamma*rstd*(mean*rstd*S1 - S0)/M
+// (S0 = sum g, S1 = sum g*yhat, recovered from the raw moment the reduce kernel accumulates)
 // and the parameter gradients dgamma = S1, dbeta = S0 (accumulated when `accumulate`).
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float* __restrict__ s1, float count,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -264,7 +272,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float g = gamma[c], r = rstd[c], m = mean[c];
-    const float S0 = s0[c], S1 = s1[c];
+    const float S0 = s0[c];
+    const float S1 = r * (s1[c] - m * S0);      // s1 holds the raw moment sum g*y: sum g*yhat = rstd*(sum g*y - mean*sum g)
     coef[c] = g * r;
     coef[C + c] = -g * r * r * S1 / count;
     coef[2 * C + c] = g * r * (m * r * S1 - S0) / count;
@@ -274,13 +283,13 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
 
 // g = dout * (out > 0);  dy = a*g + b*y + c ; optionally dys = as*g + bs*ys + cs ; optionally gout = g
 template <bool SECOND, bool WRITE_G>
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
                                     const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
                                     __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
-    __shared__ float p[8][256];
+    __shared__ __align__(16) float p[8][256];
     const bool remask = out == nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         p[6][i] = remask ? act_scale[i] : 0.f;
@@ -295,16 +304,22 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
         }
     }
     __syncthreads();
-    const int cvec = C >> 3;
+    const int c0 = static_cast<int>(threadIdx.x % (C >> 3)) << 3;   // loop-invariant: blockDim is a multiple of C/8
+    float ka[8], kb[8], kc[8];
+    lds8(p[0], c0, ka);
+    lds8(p[1], c0, kb);
+    lds8(p[2], c0, kc);
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cvec) << 3;
         F8 g = load8(dout + i * 8);
         F8 yy = load8(y + i * 8);
         F8 o, r, r2, y2;
         if (remask) {
+            float asc[8], ash[8];
+            lds8(p[6], c0, asc);
+            lds8(p[7], c0, ash);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], p[6][c0 + j], p[7][c0 + j]);
+            for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], asc[j], ash[j]);
         } else {
             o = load8(out + i * 8);
         }
@@ -313,8 +328,15 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
         for (int j = 0; j < 8; ++j) {
             const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
             g.v[j] = gj;
-            r.v[j] = fmaf(p[0][c0 + j], gj, fmaf(p[1][c0 + j], yy.v[j], p[2][c0 + j]));
-            if (SECOND) r2.v[j] = fmaf(p[3][c0 + j], gj, fmaf(p[4][c0 + j], y2.v[j], p[5][c0 + j]));
+            r.v[j] = fmaf(ka[j], gj, fmaf(kb[j], yy.v[j], kc[j]));
+        }
+        if (SECOND) {
+            float sa[8], sb[8], sc2[8];
+            lds8(p[3], c0, sa);
+            lds8(p[4], c0, sb);
+            lds8(p[5], c0, sc2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r2.v[j] = fmaf(sa[j], g.v[j], fmaf(sb[j], y2.v[j], sc2[j]));
         }
         store8(dy + i * 8, r);
         if (SECOND) store8(dys + i * 8, r2);
@@ -504,22 +526,24 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
 }
 
 extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
-                                const float* mean, const float* rstd, cvp ys,
-                                const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
-                                cudaStream_t stream) {
+                                const float* mean, const float* rstd, cvp ys, const float* mean_s,
+                                const float* rstd_s, float* sums, long long npix, int C, cudaStream_t stream) {
     HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
     HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_reduce: need `out` or the activation scale/shift");
+    (void)mean; (void)rstd; (void)mean_s; (void)rstd_s;   // the sums are raw moments; hd_bn_bwd_finalize applies mean / rstd
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
-    const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
+    const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
-    if (ys) {
-        bn_bwd_reduce_kernel<true><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), mean, rstd, BF(ys), mean_s,
-                                                                rstd_s, sums, static_cast<size_t>(npix), C);
-    } else {
-        bn_bwd_reduce_kernel<false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), mean, rstd, nullptr,
-                                                                 nullptr, nullptr, sums, static_cast<size_t>(npix), C);
-    }
+    const size_t np = static_cast<size_t>(npix);
+    if (ys && out)
+        bn_bwd_reduce_kernel<true, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C);
+    else if (ys)
+        bn_bwd_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C);
+    else if (out)
+        bn_bwd_reduce_kernel<false, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C);
+    else
+        bn_bwd_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -49,6 +49,22 @@ int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, 
                     int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                     hd_stream_t stream);
 
+/* Optional fusion of the train-mode BatchNorm finalize (hourglass.py:103) into the convolution: the last CTA to
+ * flush its statistics computes out[0..4*cout) = scale | shift | mean | rstd, updates the running statistics
+ * (momentum, unbiased variance) and num_batches_tracked. `counter` is a zero-initialised device word the kernel
+ * leaves at zero again. */
+typedef struct hd_bn_fuse {
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var; long long* num_batches_tracked;
+    float momentum, eps;
+    float* out;
+    unsigned int* counter;
+} hd_bn_fuse;
+int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                       const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
+                       int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
+                       const hd_bn_fuse* bn, hd_stream_t stream);
+
 /* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the
  * halo-reuse M=256 kernel (3x3, block_n 128, map >= 16x16) whenever the shape is eligible. */
 void hd_set_conv_variant(int variant);
@@ -104,6 +120,18 @@ int hd_bn_bwd_reduce(const void* dout, const void* out, const float* act_scale, 
                      const void* y, const float* mean, const float* rstd,
                      const void* ys, const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
                      hd_stream_t stream);
+/* Same reduction with the finalize fused in: the last block to add its partial sums also computes coef (and coef_s),
+ * dgamma / dbeta (and the skip branch's) exactly like hd_bn_bwd_finalize, then re-zeroes `sums`.
+ * `counter`: zero-initialised device word (left at zero). */
+typedef struct hd_bn_bwd_fuse {
+    const float* gamma; const float* mean; const float* rstd; float* coef; float* dgamma; float* dbeta;
+    const float* gamma_s; const float* mean_s; const float* rstd_s; float* coef_s; float* dgamma_s; float* dbeta_s;
+    float count;
+    unsigned int* counter;
+} hd_bn_bwd_fuse;
+int hd_bn_bwd_reduce_fin(const void* dout, const void* out, const float* act_scale, const float* act_shift,
+                         const void* y, const void* ys, float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin,
+                         hd_stream_t stream);
 int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
                        const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
                        hd_stream_t stream);

@@ -19,6 +19,7 @@
 // * Persistent: grid = min(tiles, #SM); tiles are taken round-robin.
 #include <cuda_bf16.h>
 
+#include "hd_b200.h"
 #include "hd_common.h"
 #include "hd_ptx.cuh"
 
@@ -46,6 +47,9 @@ struct ConvParams {
     const __nv_bfloat16* addend;  // optional NHWC bf16, same shape as out (mode 0)
     float* stat_sum;          // optional [cout] : sum over pixels of the fp32 conv output (bias included)
     float* stat_sqsum;        // optional [cout]
+    // optional fused train-mode BN finalize by the last CTA to flush its statistics (see hd_bn_fuse in hd_b200.h)
+    const float* bn_gamma; const float* bn_beta; float* bn_rm; float* bn_rv; long long* bn_nbt;
+    float bn_momentum, bn_eps, bn_count; float* bn_out; unsigned int* bn_counter;
     int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
                               // 2 = MMA issue skipped, 3 = weight tiles loaded only for the first tile
 };
@@ -149,6 +153,47 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
             atomicAdd(&s_stat[c0 + lane], s1);
             atomicAdd(&s_stat[BLOCK_N + c0 + lane], s2);
         }
+    }
+}
+
+
+// Flush this CTA's per-channel statistics to global memory; the LAST CTA of the grid to do so (atomic ticket) turns the
+// complete statistics into the BatchNorm scale / shift / mean / rstd and updates the running statistics - the
+// separate finalize launch of hourglass.py:103's train-mode BN disappears. Called by the `nthr` epilogue threads
+// (t = 0..nthr-1), which share named barrier 1.
+template <int BLOCK_N>
+__device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stat, int t, int nthr, int* s_flag) {
+    named_bar_sync(1, nthr);
+    if (t < p.cout) {
+        atomicAdd(p.stat_sum + t, s_stat[t]);
+        atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
+    }
+    if (p.bn_out == nullptr) return;
+    __threadfence();
+    named_bar_sync(1, nthr);
+    if (t == 0) *s_flag = (atomicAdd(p.bn_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    named_bar_sync(1, nthr);
+    if (*s_flag == 0) return;
+    __threadfence();
+    if (t < p.cout) {
+        const float sum = __ldcg(p.stat_sum + t), sq = __ldcg(p.stat_sqsum + t);
+        const float mean = sum / p.bn_count;
+        const float var = fmaxf(sq / p.bn_count - mean * mean, 0.f);
+        if (p.bn_rm) {
+            const float unbiased = p.bn_count > 1.f ? var * (p.bn_count / (p.bn_count - 1.f)) : var;
+            p.bn_rm[t] = (1.f - p.bn_momentum) * p.bn_rm[t] + p.bn_momentum * mean;
+            p.bn_rv[t] = (1.f - p.bn_momentum) * p.bn_rv[t] + p.bn_momentum * unbiased;
+        }
+        const float rstd = rsqrtf(var + p.bn_eps);
+        const float sc = p.bn_gamma[t] * rstd;
+        p.bn_out[t] = sc;
+        p.bn_out[p.cout + t] = p.bn_beta[t] - mean * sc;
+        p.bn_out[2 * p.cout + t] = mean;
+        p.bn_out[3 * p.cout + t] = rstd;
+    }
+    if (t == 0) {
+        if (p.bn_nbt) *p.bn_nbt += 1;
+        *p.bn_counter = 0u;
     }
 }
 
@@ -317,16 +362,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
-        if (do_stats) {
-            named_bar_sync(1, 128);
-            const int t = threadIdx.x - 128;
-            for (int c = t; c < BLOCK_N; c += 128) {
-                if (c < p.cout) {
-                    atomicAdd(p.stat_sum + c, s_stat[c]);
-                    atomicAdd(p.stat_sqsum + c, s_stat[BLOCK_N + c]);
-                }
-            }
-        }
+        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 128, reinterpret_cast<int*>(tmem_slot + 1));
     }
 
     tc_fence_before();
@@ -502,14 +538,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
-        if (do_stats) {
-            named_bar_sync(1, 256);
-            const int t = threadIdx.x - 128;
-            if (t < p.cout) {
-                atomicAdd(p.stat_sum + t, s_stat[t]);
-                atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
-            }
-        }
+        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 256, reinterpret_cast<int*>(tmem_slot + 1));
     }
     tc_fence_before();
     __syncthreads();
@@ -662,14 +691,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             tc_fence_before();
             mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
         }
-        if (do_stats) {
-            named_bar_sync(1, 128);
-            const int t = threadIdx.x - 128;
-            if (t < p.cout) {
-                atomicAdd(p.stat_sum + t, s_stat[t]);
-                atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
-            }
-        }
+        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 128, reinterpret_cast<int*>(tmem_slot + 1));
     }
     tc_fence_before();
     __syncthreads();
@@ -718,12 +740,27 @@ extern "C" void hd_set_conv_variant(int v) { hd::g_conv_variant = v; }
 // Profiling only: see ConvParams::dbg (results are wrong when non-zero).
 extern "C" void hd_set_conv_debug(int v) { hd::g_conv_debug = v; }
 
+extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                                  const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
+                                  int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs,
+                                  int stack_idx, int num_stack, const hd_bn_fuse* bn, cudaStream_t stream);
+
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
                                const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
                                int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx,
                                int num_stack, cudaStream_t stream) {
+    return hd_conv2d_igemm_bn(x, w_packed, out, out2, bias, addend, stat_sum, stat_sqsum, N, H, W, cin, cout, block_n,
+                              ksize, out_mode, out_cs, out2_cs, stack_idx, num_stack, nullptr, stream);
+}
+
+extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                                  const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
+                                  int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs,
+                                  int stack_idx, int num_stack, const hd_bn_fuse* bn, cudaStream_t stream) {
     using namespace hd;
+    HD_REQUIRE(bn == nullptr || (stat_sum != nullptr && bn->out && bn->counter && bn->gamma && bn->beta),
+               "conv_igemm: fused BN finalize needs statistics, gamma/beta, an output block and a ticket counter");
     HD_REQUIRE(cin % 64 == 0 && cin >= 64 && cin <= 512, "conv_igemm: cin=%d must be a multiple of 64", cin);
     HD_REQUIRE(block_n == 128 || block_n == 64 || block_n == 16, "conv_igemm: block_n=%d unsupported", block_n);
     HD_REQUIRE(cout >= 1 && cout <= block_n, "conv_igemm: cout=%d > block_n=%d", cout, block_n);
@@ -751,6 +788,11 @@ extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, v
     p.bias = bias; p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
     p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
     p.dbg = g_conv_debug;
+    if (bn) {
+        p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_rm = bn->running_mean; p.bn_rv = bn->running_var;
+        p.bn_nbt = bn->num_batches_tracked; p.bn_momentum = bn->momentum; p.bn_eps = bn->eps;
+        p.bn_count = static_cast<float>(N) * H * W; p.bn_out = bn->out; p.bn_counter = bn->counter;
+    }
 
     // halo variant: 3x3, 128 output channels, map >= 16x16 and enough 16x16 tiles to fill the machine
     bool halo = false, pair = false;

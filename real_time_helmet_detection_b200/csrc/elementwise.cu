@@ -7,6 +7,7 @@
 // Per-channel BN statistics themselves are produced by the conv epilogue (conv_igemm.cu).
 #include <cuda_bf16.h>
 
+#include "hd_b200.h"
 #include "hd_common.h"
 
 namespace hd {
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
-                     float* __restrict__ sums, size_t npix, int C) {
+                     float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin) {
     extern __shared__ __align__(16) float red[];  // [3][C]
     const int cvec = C >> 3;
     const int lane_c = threadIdx.x % cvec;          // which 8-channel vector
@@ -259,6 +260,41 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         atomicAdd(sums + C + c, red[C + c]);
         if (SECOND) atomicAdd(sums + 2 * C + c, red[2 * C + c]);
     }
+    if (fin.coef == nullptr) return;
+    // fused finalize: the last block to add its partial sums builds dy = a*g + b*y + c and dgamma / dbeta
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float S0 = __ldcg(sums + c);
+        {
+            const float g = fin.gamma[c], r = fin.rstd[c], m = fin.mean[c];
+            const float S1 = r * (__ldcg(sums + C + c) - m * S0);
+            fin.coef[c] = g * r;
+            fin.coef[C + c] = -g * r * r * S1 / fin.count;
+            fin.coef[2 * C + c] = g * r * (m * r * S1 - S0) / fin.count;
+            if (fin.dgamma) fin.dgamma[c] = S1;
+            if (fin.dbeta) fin.dbeta[c] = S0;
+        }
+        if (SECOND) {
+            const float g = fin.gamma_s[c], r = fin.rstd_s[c], m = fin.mean_s[c];
+            const float S1 = r * (__ldcg(sums + 2 * C + c) - m * S0);
+            fin.coef_s[c] = g * r;
+            fin.coef_s[C + c] = -g * r * r * S1 / fin.count;
+            fin.coef_s[2 * C + c] = g * r * (m * r * S1 - S0) / fin.count;
+            if (fin.dgamma_s) fin.dgamma_s[c] = S1;
+            if (fin.dbeta_s) fin.dbeta_s[c] = S0;
+        }
+        // leave the accumulators zeroed for the next reduction that uses this scratch block (stream-ordered)
+        sums[c] = 0.f;
+        sums[C + c] = 0.f;
+        if (SECOND) sums[2 * C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
 // From the reduction sums build the per-channel affine form of the BN input gradient
@@ -525,25 +561,40 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     return HD_OK;
 }
 
+extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y, cvp ys,
+                                    float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin, cudaStream_t stream);
+
 extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
                                 const float* mean, const float* rstd, cvp ys, const float* mean_s,
                                 const float* rstd_s, float* sums, long long npix, int C, cudaStream_t stream) {
+    (void)mean; (void)rstd; (void)mean_s; (void)rstd_s;   // the sums are raw moments; hd_bn_bwd_finalize applies mean / rstd
+    return hd_bn_bwd_reduce_fin(dout, out, act_scale, act_shift, y, ys, sums, npix, C, nullptr, stream);
+}
+
+extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y, cvp ys,
+                                    float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin_in,
+                                    cudaStream_t stream) {
+    hd_bn_bwd_fuse fin{};
+    if (fin_in) fin = *fin_in;
+    HD_REQUIRE(fin.coef == nullptr || (fin.counter && fin.gamma && fin.mean && fin.rstd && fin.count > 0.f),
+               "bn_bwd_reduce: fused finalize needs gamma / mean / rstd / count and a ticket counter");
+    HD_REQUIRE(fin.coef == nullptr || ys == nullptr || (fin.coef_s && fin.gamma_s && fin.mean_s && fin.rstd_s),
+               "bn_bwd_reduce: fused finalize of the skip branch needs its gamma / mean / rstd / coef");
     HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
     HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_reduce: need `out` or the activation scale/shift");
-    (void)mean; (void)rstd; (void)mean_s; (void)rstd_s;   // the sums are raw moments; hd_bn_bwd_finalize applies mean / rstd
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
     if (ys && out)
-        bn_bwd_reduce_kernel<true, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C);
+        bn_bwd_reduce_kernel<true, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin);
     else if (ys)
-        bn_bwd_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C);
+        bn_bwd_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin);
     else if (out)
-        bn_bwd_reduce_kernel<false, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C);
+        bn_bwd_reduce_kernel<false, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C, fin);
     else
-        bn_bwd_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C);
+        bn_bwd_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C, fin);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

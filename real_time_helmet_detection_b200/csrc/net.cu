@@ -97,6 +97,7 @@ struct hd_net {
     size_t wgrad_ws_bytes = 0;
     float* small = nullptr;   // scratch for BN-backward sums / coefficients
     void* pack_jobs_dev = nullptr;          // device copy of the weight-pack job table
+    unsigned int* tickets = nullptr;        // one zeroed word per unit: "last CTA finalizes the BN" ticket counters
     // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
     // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
     Arena wg;
@@ -195,7 +196,9 @@ static void plan_persistent(hd_net* n) {
     Arena& a = n->persist;
     size_t stats_total = 0;
     for (Unit& u : n->units) stats_total += 2 * static_cast<size_t>(u.cout);
-    float* stats = reinterpret_cast<float*>(a.alloc(stats_total * sizeof(float)));
+    // statistics and ticket counters are contiguous: one memset per forward clears both
+    float* stats = reinterpret_cast<float*>(a.alloc((stats_total + n->units.size() + 64) * sizeof(float)));
+    n->tickets = stats ? reinterpret_cast<unsigned int*>(stats + stats_total) : nullptr;
     size_t so = 0;
     for (Unit& u : n->units) {
         u.stats = stats ? stats + so : nullptr;
@@ -215,7 +218,7 @@ static void plan_persistent(hd_net* n) {
     n->small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->alt.small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->pack_jobs_dev = a.alloc(2 * n->units.size() * 64);
-    n->persist_bytes = stats_total * sizeof(float);
+    n->persist_bytes = (stats_total + n->units.size()) * sizeof(float);
 }
 
 // Host mirror of hd::PackJob (csrc/pack.cu).
@@ -298,9 +301,18 @@ static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, i
     const int k = u.kind == 1 ? 1 : u.k;
     const bool stats = u.bn && training;
     u.npix = static_cast<long long>(B) * H * W;
-    RUN(hd_conv2d_igemm(x, u.wp, y, nullptr, u.bias ? p.b : nullptr, addend, stats ? u.stats : nullptr,
-                        stats ? u.stats + u.cout : nullptr, B, H, W, cin_gemm, u.cout, block_n_for(u.cout), k, 0,
-                        u.cout, 0, 0, 1, n->stream));
+    if (stats) {
+        // train mode: the conv's last CTA finalizes the BN (scale/shift/mean/rstd + running statistics) itself
+        hd_bn_fuse bn{};
+        bn.gamma = p.gamma; bn.beta = p.beta; bn.running_mean = p.running_mean; bn.running_var = p.running_var;
+        bn.num_batches_tracked = p.num_batches_tracked; bn.momentum = 0.1f; bn.eps = 1e-5f;
+        bn.out = u.bnp; bn.counter = n->tickets + ui;
+        RUN(hd_conv2d_igemm_bn(x, u.wp, y, nullptr, u.bias ? p.b : nullptr, addend, u.stats, u.stats + u.cout, B, H, W,
+                               cin_gemm, u.cout, block_n_for(u.cout), k, 0, u.cout, 0, 0, 1, &bn, n->stream));
+        return;
+    }
+    RUN(hd_conv2d_igemm(x, u.wp, y, nullptr, u.bias ? p.b : nullptr, addend, nullptr, nullptr, B, H, W, cin_gemm, u.cout,
+                        block_n_for(u.cout), k, 0, u.cout, 0, 0, 1, n->stream));
     if (u.bn)
         RUN(hd_bn_finalize(u.stats, u.stats + u.cout, static_cast<float>(u.npix), p.gamma, p.beta, p.running_mean,
                            p.running_var, p.num_batches_tracked, 0.1f, 1e-5f, training, u.bnp, u.bnp + u.cout,
@@ -361,6 +373,9 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     if (!n->dry) {
         if (n->rc == 0 && cudaMemsetAsync(n->units[0].stats, 0, n->persist_bytes, n->stream) != cudaSuccess)
             n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN statistics failed");
+        if (n->rc == 0 && (cudaMemsetAsync(n->small, 0, 16 * 256 * sizeof(float), n->stream) != cudaSuccess ||
+                           cudaMemsetAsync(n->alt.small, 0, 16 * 256 * sizeof(float), n->stream) != cudaSuccess))
+            n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN-backward scratch failed");
         pack_weights(n, training != 0);
     }
     // ---- PreLayer (hourglass.py:159-173)
@@ -434,21 +449,22 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
     float* sums = n->small;            // [3][C]
     float* coef = n->small + 3 * 256;  // [3][C]
     float* coef_s = n->small + 6 * 256;
-    if (!n->dry && n->rc == 0 && cudaMemsetAsync(sums, 0, 3 * C * sizeof(float), n->stream) != cudaSuccess)
-        n->rc = fail(HD_ERR_CUDA, "net_backward: memset failed");
+    // `sums` and the ticket counter are zeroed once per forward pass and re-zeroed by the fused finalize after use
     const float* mean = u.bnp + 2 * C;
     const float* rstd = u.bnp + 3 * C;
     const Unit* s = us >= 0 ? &n->units[us] : nullptr;
-    // out == nullptr: plain conv+BN+ReLU unit, the mask is recomputed from y and this unit's scale/shift
-    RUN(hd_bn_bwd_reduce(dout, out, u.bnp, u.bnp + C, y, mean, rstd, ys, s ? s->bnp + 2 * C : nullptr,
-                         s ? s->bnp + 3 * C : nullptr, sums, u.npix, C, n->stream));
-    RUN(hd_bn_bwd_finalize(sums, sums + C, static_cast<float>(u.npix), p.gamma, mean, rstd, coef, p.dgamma, p.dbeta, 0,
-                           C, n->stream));
+    // out == nullptr: plain conv+BN+ReLU unit, the mask is recomputed from y and this unit's scale/shift.
+    // The reduction's last block also produces the coefficients and dgamma / dbeta (no separate finalize launch).
+    hd_bn_bwd_fuse fin{};
+    fin.gamma = p.gamma; fin.mean = mean; fin.rstd = rstd; fin.coef = coef; fin.dgamma = p.dgamma; fin.dbeta = p.dbeta;
+    fin.count = static_cast<float>(u.npix);
+    fin.counter = reinterpret_cast<unsigned int*>(n->small + 9 * 256);
     if (s) {
         const hd_unit_ptrs& ps = UP(n, us);
-        RUN(hd_bn_bwd_finalize(sums, sums + 2 * C, static_cast<float>(u.npix), ps.gamma, s->bnp + 2 * C,
-                               s->bnp + 3 * C, coef_s, ps.dgamma, ps.dbeta, 0, C, n->stream));
+        fin.gamma_s = ps.gamma; fin.mean_s = s->bnp + 2 * C; fin.rstd_s = s->bnp + 3 * C; fin.coef_s = coef_s;
+        fin.dgamma_s = ps.dgamma; fin.dbeta_s = ps.dbeta;
     }
+    RUN(hd_bn_bwd_reduce_fin(dout, out, u.bnp, u.bnp + C, y, ys, sums, u.npix, C, &fin, n->stream));
     RUN(hd_bn_bwd_apply(dout, out, u.bnp, u.bnp + C, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout, u.npix, C,
                         n->stream));
 }

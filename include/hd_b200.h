@@ -84,6 +84,9 @@ size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int ksize);
 /* OIHW fp32 -> packed bf16 UMMA operand. mode 0: forward [tap][co][ci]; mode 1: dgrad [tap'][ci][co] (rotated). */
 int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int cin, int ksize, int rows_pad, int k_pad,
                         int mode, hd_stream_t stream);
+/* All weights of a network in one launch; `jobs` is a DEVICE table of {const float* w; bf16* out; int cout, cin, taps,
+ * rows_pad, k_pad, mode (0 fwd, 1 dgrad, 2 stem); long long start} with ascending `start` (flat output offset). */
+int hd_pack_all_weights(const void* jobs, int njobs, long long total, hd_stream_t stream);
 int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int c_pad, hd_stream_t stream);
 int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, int c_stride, hd_stream_t stream);
 
@@ -171,6 +174,16 @@ int hd_decode_nms(const float* heat, long long bs_heat, long long ss_heat, const
                   int W, int topk, float scale_factor, float conf_th, float nms_th, int normalized,
                   int apply_sigmoid, int do_nms, void* scratch, float* out_boxes, long long* out_cls,
                   float* out_scores, int* out_count, hd_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer (optim.py:3-12, train.py:128-139) */
+
+/* Fused multi-tensor Adam: one launch over all tensors. jobs_host: njobs records {float* p; const float* g; float* m;
+ * float* v; long long n; long long chunk_start} (chunks of 1024 elements, ascending); jobs_dev: device scratch of the
+ * same size; step_dev: device float = steps taken so far (advanced here); grad_scale / found_inf: optional device
+ * floats of torch.amp.GradScaler (gradients are multiplied by 1/grad_scale; nothing happens when found_inf != 0). */
+int hd_adam_step(const void* jobs_host, int njobs, void* jobs_dev, long long nchunks, float lr, float beta1,
+                 float beta2, float eps, float* step_dev, const float* grad_scale, const float* found_inf,
+                 hd_stream_t stream);
 
 /* ------------------------------------------------------------------ whole-network executor (hourglass.py:198-237) */
 

@@ -236,6 +236,28 @@ def decode_latency(torch, dev, S=1, runs=300):
             "algorithmic_bytes": 6 * H * W * 4 * S, "reference_cpu_us": "1450 (BASELINE.md, 8 vCPU Xeon, this container)"}
 
 
+def inference_latency(torch, dev, S=1, runs=50):
+    """Batch-1 inference as the reference's demo times it (PytorchToCpp/main.cpp:60-67, README.md:76: "100 FPS" on a
+    GTX 1080 Ti): network forward (eval mode) + fused decode/NMS, host wall clock ending with the result read-back."""
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.evaluate import Prediction
+    torch.manual_seed(0)
+    net = StackedHourglass(S, 128, 6).to(dev).eval()
+    pred = Prediction(net, topk=100, scale_factor=4, conf_th=0.2, nms="nms", nms_th=0.2)
+    x = torch.randn(1, 3, 512, 512, device=dev)
+    for _ in range(5):
+        pred(x)
+    torch.cuda.synchronize()
+    wall = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        pred(x)
+        wall.append(time.perf_counter() - t0)
+    ms = statistics.median(wall) * 1e3
+    return {"workload": f"forward (eval) + decode + NMS, 512x512 batch 1, {S} stack", "ms": ms, "fps": 1e3 / ms,
+            "reference": "README.md:76: 100 FPS (10 ms) on a GTX 1080 Ti, TorchScript C++ app"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -347,6 +369,7 @@ def run_ours(args):
         roof["step_frac_of_conv_roofline"] = step_frac
         roof["step_peak"] = f"{peaks['bf16_tflops_sustained']} TFLOP/s sustained ({peaks['source']})"
         dec = decode_latency(torch, dev, S=1)
+        infer = inference_latency(torch, dev, S=1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ips, dt, cores = time_cpu(torch, S, size, 2, 4, 1)
@@ -364,7 +387,8 @@ def run_ours(args):
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
                         "how": "train.train_step on pinned host batches via train.DevicePrefetcher (H2D of step i+1 "
                                "overlaps step i); every step's loss is copied D2H and read on the host one step later"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "decode": dec}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "decode": dec,
+                "inference_b1": infer}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if hook is not None:

@@ -76,9 +76,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
 // epilogue alone took 78 us of a 123 us kernel). Staged, one instruction writes 8 rows x 64 contiguous bytes.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t taddr, bool valid, size_t pix, uint32_t lane,
-                                              float* s_stat, bool do_stats, uint8_t* stage) {
+                                              float* s_stat, bool do_stats, uint8_t* stage, int c_begin = 0,
+                                              int c_end = BLOCK_N) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t r[32];
         tmem_ld_x32(taddr + c0, r);
         tmem_ld_wait();
@@ -197,10 +198,13 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stat, 
     }
 }
 
+// BLOCK_N >= 64 runs with EIGHT epilogue warps (384 threads): warps 4-7 drain the first half of the columns, warps 8-11
+// the second half - with few k-steps per tile (1x1 convs, the K=192 stem, N=64) the epilogue is the pacing stage.
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BLOCK_N >= 64 ? 384 : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const ConvParams p) {
+    constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;
     constexpr int kBBytes = BLOCK_N * 128;
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
@@ -215,7 +219,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint64_t* tmem_empty = bars + 2 * kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BLOCK_N]
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [4 epilogue warps][2 KB]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [epilogue warps][2 KB]
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -231,7 +235,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], 32 * kEpiWarps);
         }
         fence_mbar_init();
     }
@@ -319,7 +323,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (BLOCK_N >= 32) {
-                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
+                constexpr int kHalf = kEpiWarps == 8 ? BLOCK_N / 2 : BLOCK_N;
+                const int cb = ((warp - 4) >> 2) * kHalf;
+                epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048, cb,
+                                       cb + kHalf);
             } else {
                 // BLOCK_N == 16: prediction head (hourglass.py:189-195), fp32 NCHW logits
                 uint32_t r[16];
@@ -362,7 +369,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
-        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 128, reinterpret_cast<int*>(tmem_slot + 1));
+        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 32 * kEpiWarps, reinterpret_cast<int*>(tmem_slot + 1));
     }
 
     tc_fence_before();
@@ -374,7 +381,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kStages * (kABytes + BLOCK_N * 128) + 1024 /*align*/ + 256 /*barriers*/ +
-                               2 * BLOCK_N * 4 + 4 * 2048 /*store staging*/;
+                               2 * BLOCK_N * 4 + 8 * 2048 /*store staging*/;
     static bool attr_set = false;
     if (!attr_set) {
         HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -382,7 +389,7 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_igemm_kernel<BLOCK_N><<<grid, kThreads, smem_bytes, stream>>>(tx, tw, p);
+    conv_igemm_kernel<BLOCK_N><<<grid, BLOCK_N >= 64 ? 384 : kThreads, smem_bytes, stream>>>(tx, tw, p);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -193,13 +193,13 @@ def dominant_kernel_roofline(torch, dev, peaks, reps=20):
     flops = 2.0 * B * H * W * C * C * 9
     achieved = flops / dt / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "conv_igemm_kernel<128> 3x3 128->128 @128x128 B=32 (fwd, BN-stat epilogue)",
+    return {"bound": "tensor", "kernel": "conv_igemm_halo_kernel 3x3 128->128 @128x128 B=32 (fwd, BN-stat epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)", "us_per_launch": dt * 1e6,
             "flops_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
             # (profiles/r01_conv_igemm_halo_ncu_full.txt); algorithmic bytes = 134.2 MB in + 134.2 MB out + 0.3 MB weights
-            "traffic": 225.3e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 268.7e6}
+            "traffic": 226.6e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 268.7e6}
 
 
 def decode_latency(torch, dev, S=1, runs=300):

@@ -175,6 +175,23 @@ int hd_decode_nms(const float* heat, long long bs_heat, long long ss_heat, const
                   int apply_sigmoid, int do_nms, void* scratch, float* out_boxes, long long* out_cls,
                   float* out_scores, int* out_count, hd_stream_t stream);
 
+/* ------------------------------------------------------------------ GT encoder + input normalisation (8(f)-2) */
+
+/* box2hm + draw_gaussian (transform.py:4-70) for a whole batch, as data.py:108-115 calls it from collate_fn, on the
+ * device: boxes [B][nmax][4] fp32 (xmin, ymin, xmax, ymax in input pixels), labels [B][nmax] int32 (< 0: empty slot,
+ * the reference's `box is None`), nmax <= 128. Outputs (fp32, fully written): heat [B][num_cls][h][w],
+ * offset / size [B][2][h][w], mask [B][1][h][w]; h = imsize_y / scale_factor, w = imsize_x / scale_factor.
+ * Boxes are applied in list order (the last box owning a centre cell wins, heat is the running maximum). A box whose
+ * centre cell falls outside the map (IndexError / negative-index wrap-around in the reference) or whose label is
+ * >= num_cls is skipped and counted in *err_count (optional device int, caller-zeroed). */
+int hd_encode_targets(const float* boxes, const int* labels, int B, int nmax, int h, int w, int num_cls,
+                      int scale_factor, int normalized, float* heat, float* offset, float* size, float* mask,
+                      int* err_count, hd_stream_t stream);
+/* TF.to_tensor + torchvision Normalize (data.py:118, utils.py:55-68): uint8 [B][H][W][3] -> fp32 [B][3][H][W],
+ * ((u8 / 255) - mean[c]) / std[c] in fp32 with IEEE division. mean3 / std3 are HOST arrays of 3 floats. */
+int hd_normalize_u8(const void* img_nhwc_u8, float* out_nchw, int B, int H, int W, const float* mean3,
+                    const float* std3, hd_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer (optim.py:3-12, train.py:128-139) */
 
 /* Fused multi-tensor Adam: one launch over all tensors. jobs_host: njobs records {float* p; const float* g; float* m;

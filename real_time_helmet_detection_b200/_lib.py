@@ -52,6 +52,8 @@ _SIGNATURES = {
     "hd_loss_forward": (I, [P, LL, P, LL, P, LL, P, P, P, P, I, I, I, I, F, F, F, F, F, I, I, P, P, P]),
     "hd_loss_backward": (I, [P, LL, P, LL, P, LL, P, P, P, P, I, I, I, I, F, F, F, F, F, I, I, P, P,
                              P, LL, P, LL, P, LL, P]),
+    "hd_encode_targets": (I, [P, P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
+    "hd_normalize_u8": (I, [P, P, I, I, I, P, P, P]),
     "hd_decode_scratch_bytes": (c_size_t, [I, I, I, I, I]),
     "hd_decode_nms": (I, [P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, I, I, I, F, F, F, I, I, I, P, P, P, P, P, P]),
 }

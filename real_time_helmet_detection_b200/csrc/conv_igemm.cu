@@ -51,7 +51,7 @@ struct ConvParams {
     const float* bn_gamma; const float* bn_beta; float* bn_rm; float* bn_rv; long long* bn_nbt;
     float bn_momentum, bn_eps, bn_count; float* bn_out; unsigned int* bn_counter;
     int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
-                              // 2 = MMA issue skipped, 3 = weight tiles loaded only for the first tile
+                              // 2 = MMA issue skipped (halo kernel only)
 };
 
 // Sum v[0..31] across the 32 lanes of the warp; on return lane l holds the total of element l.
@@ -395,32 +395,110 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// "Halo" variant for the FLOP-dominant case (3x3, 128 output channels, maps >= 16x16): the generic kernel above
+// "Halo" kernel for the FLOP-dominant case (3x3, 128 output channels, maps >= 16x16): the generic kernel above
 // re-fetches the activation tile for each of the 9 taps and the weights for every 128-pixel tile, which makes it
-// L2->SM bandwidth bound (measured 14.3 TB/s, ~54 % of the tensor peak). Here a CTA tile is 16x16 pixels (M = 256:
-// two 128-row accumulators sharing every weight tile), and for each dx ONE activation box of 18 rows x 16 columns is
-// loaded; the three dy taps read that tile at a row offset of dy*16 pixels = dy*2048 B (whole 8-row swizzle groups,
-// so only the UMMA descriptor start address moves). L2->SM bytes per FLOP drop 2.3x.
+// L2->SM bandwidth bound (measured 14.3 TB/s, ~54 % of the tensor peak). Here a CTA tile is 16x16 pixels and for each dx
+// ONE activation box of 18 rows x 16 columns is loaded; the three dy taps read that box at a row offset of dy*16
+// pixels = dy*2048 B (whole 8-row swizzle groups, so only the UMMA descriptor start address moves). L2->SM bytes per
+// FLOP drop 2.3x.
 constexpr int kHARows = 18 * 16;
 constexpr int kHABytes = kHARows * 128;   // 36,864
 constexpr int kHAStages = 3;
 constexpr int kHBBytes = 128 * 128;       // one (tap, 64-channel chunk) weight tile for 128 output channels
 constexpr int kHBStages = 5;
 
-// 12 warps: producer, MMA issuer, TMEM allocator, (idle), and EIGHT epilogue warps - warps 4-7 drain accumulator half 0,
-// warps 8-11 half 1 (a warp may only touch the TMEM lane quarter warp_idx % 4). With four warps the BN-statistics
-// epilogue (62 shuffles per 32 columns) was the pacing stage: 148 us with statistics vs 119 us without.
+// 12 warps: producer, MMA issuer, TMEM allocator, (idle), and EIGHT epilogue warps - warps 4-7 drain pixel half 0,
+// warps 8-11 half 1 (a warp may only touch the TMEM lane quarter warp_idx % 4).
 constexpr int kHaloThreads = 384;
+
+// The product is computed TRANSPOSED: D^T[cout, pixel] = W[cout, k] * X^T[k, pixel]. The weights are the A operand
+// (M = 128 output channels), the 16x16-pixel activation tile is the B operand (N = 256), so one tcgen05.mma (M128 N256
+// K16, 128 cycles) does the work of two M128 N128 ones and the tensor core re-reads 4 KB of weights + 8 KB of
+// activations per 128 cycles instead of 2 x (4 + 4) KB: shared-memory operand traffic drops from 128 to 96 B/clk per SM.
+// The first halo kernel (pixels as M, two 128-row accumulators) was paced by exactly that port: 116-126 us per launch
+// at 128^2 x B32, 108 us with the epilogue switched off; this one: 105-109 us, 92 us without epilogue (round-1 ncu).
+// The accumulator is [lane = output channel][column = pixel]:
+//   * BN statistics are per-THREAD running sums (a thread owns one channel) - the 62-shuffle transposing reduction of
+//     epilogue_rows() disappears;
+//   * the NHWC store needs a transpose. The SM's L1/shared-memory data pipe is the contended resource (ncu: tensor-core
+//     operand reads 55 % + LSU 37 % of its peak with a naive staged transpose: 2-byte STS, LDS.128, STG.128), so the
+//     transpose costs as few wavefronts as possible: one shuffle per pixel pair inside lane pairs, 16 conflict-free
+//     32-bit STS per 32x32 block into a [pixel][channel] staging tile, and a TMA bulk-tensor STORE of that tile (which
+//     also clips at the image border) instead of LDS + STG.
+// What remains between 92 and ~106 us is the epilogue's TMEM read (128 KB of fp32 accumulators per tile at 64 B/clk
+// = 2048 of the tile's 9216 MMA cycles), which the tensor core's own accumulator traffic has to share.
+__device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUtensorMap* tmap_o, uint32_t taddr, int cbase,
+                                                 uint32_t lane, int n, int x0, int yb, uint8_t* stage, float bias,
+                                                 bool do_stats, float& s1, float& s2) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr, r);
+    // Lane pair (2m, 2m+1) = channels (c, c+1). For the pixel pair (2j, 2j+1) the even lane ends up with both channels
+    // of pixel 2j and the odd lane with both channels of pixel 2j+1 (one shuffle), i.e. one packed bf16x2 word each.
+    const uint32_t odd = lane & 1u;
+    uint32_t add[16];
+    if (p.addend) {
+        const int cpair = cbase + static_cast<int>(lane & ~1u);
+        const size_t row0 = (static_cast<size_t>(n) * p.H + yb) * p.W;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int x = x0 + ((2 * j) & 15) + static_cast<int>(odd);
+            add[j] = 0u;
+            if (yb + (j >> 3) < p.H && x < p.W)
+                add[j] = __ldg(reinterpret_cast<const uint32_t*>(p.addend + (row0 + (j >> 3) * p.W + x) * p.out_cs + cpair));
+        }
+    }
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias;
+    if (p.addend) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, add[j], 1);
+            // even lane (channel c): c @ pixel 2j = low half of its own word, c @ 2j+1 = low half of the partner's;
+            // odd lane (channel c+1): @ 2j = high half of the partner's word, @ 2j+1 = high half of its own
+            const uint32_t w0 = odd ? other : add[j], w1 = odd ? add[j] : other;
+            v[2 * j] += __uint_as_float(odd ? (w0 & 0xffff0000u) : (w0 << 16));
+            v[2 * j + 1] += __uint_as_float(odd ? (w1 & 0xffff0000u) : (w1 << 16));
+        }
+    }
+    // the previous TMA store of this warp must have finished reading the staging buffer before it is overwritten
+    if (lane == 0) bulk_wait_group_read<0>();
+    __syncwarp();
+    // staging tile [32 pixels][32 channels] bf16 = the store box {32 ch, 16 x, 2 y}: even lanes fill pixel row 2j, odd
+    // lanes row 2j+1, 16 consecutive words each -> one conflict-free 128-byte wavefront per instruction
+    uint32_t* srow = reinterpret_cast<uint32_t*>(stage) + odd * 16 + (lane >> 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[2 * j] : v[2 * j + 1], 1);
+        srow[32 * j] = odd ? pack_bf16x2(recv, v[2 * j + 1]) : pack_bf16x2(v[2 * j], recv);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_4d(tmap_o, stage, cbase, x0, yb, n);     // clipped at the image border by the TMA unit
+        bulk_commit_group();
+    }
+    if (do_stats) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const bool ok = (yb + (i >> 4) < p.H) && (x0 + (i & 15) < p.W);
+            const float t = ok ? v[i] : 0.f;
+            s1 += t;
+            s2 = fmaf(t, t, s2);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                       const ConvParams p) {
-    constexpr int BLOCK_N = 128;
-    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0);
+                        const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
+    constexpr int BLOCK_N = 128;                                   // output channels (the MMA's M here)
+    constexpr uint32_t kIdesc = umma_idesc_bf16(256, 0, 0);        // M = 128 channels, N = 256 pixels
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kHAStages * kHABytes;
+    uint8_t* smem_a = smem;                                        // activation ring (B operand)
+    uint8_t* smem_b = smem + kHAStages * kHABytes;                 // weight ring (A operand)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kHBStages * kHBBytes);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kHAStages;
@@ -430,13 +508,14 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128]
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [8 epilogue warps][2 KB]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 127) & ~uintptr_t(127));   // [8 epilogue warps][2 KB], TMA store source
 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_o);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < kHAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -466,11 +545,6 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         tma_load_4d(smem_a + sa * kHABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - 1, y0 - 1, n);
                         for (int dy = 0; dy < 3; ++dy) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
-                            if (p.dbg == 3 && tile != static_cast<int>(blockIdx.x)) {
-                                mbar_arrive(&b_full[sb]);
-                                if (++sb == kHBStages) { sb = 0; pb ^= 1; }
-                                continue;
-                            }
                             mbar_arrive_expect_tx(&b_full[sb], kHBBytes);
                             tma_load_3d(smem_b + sb * kHBBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * 3 + dx);
                             if (++sb == kHBStages) { sb = 0; pb ^= 1; }
@@ -491,22 +565,18 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             for (int dx = 0; dx < 3; ++dx) {
                 for (int ck = 0; ck < p.cin_chunks; ++ck) {
                     mbar_wait(&a_full[sa], pa);
-                    const uint32_t a_addr = smem_u32(smem_a + sa * kHABytes);
+                    const uint32_t x_addr = smem_u32(smem_a + sa * kHABytes);
                     for (int dy = 0; dy < 3; ++dy) {
                         mbar_wait(&b_full[sb], pb);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + sb * kHBBytes), 0, 1024);
+                            const uint64_t wdesc = umma_smem_desc_sw128(smem_u32(smem_b + sb * kHBBytes), 0, 1024);
+                            // 256 pixel rows of the box starting dy rows down: 16 tile rows x 16 columns, 32 KB contiguous
+                            const uint64_t xdesc = umma_smem_desc_sw128(x_addr + dy * 2048, 0, 1024);
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                // rows of accumulator h = tile rows 8h..8h+7, shifted down by dy: (dy + 8h) * 16 pixels
-                                const uint64_t adesc = umma_smem_desc_sw128(a_addr + (dy + 8 * h) * 2048, 0, 1024);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (p.dbg != 2)
-                                        umma_bf16(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, kIdesc,
-                                                  (first && k == 0) ? 0u : 1u);
-                            }
+                            for (int k = 0; k < 4; ++k)
+                                if (p.dbg != 2)
+                                    umma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
                             umma_commit(&b_empty[sb]);
                         }
                         __syncwarp();
@@ -522,9 +592,13 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             __syncwarp();
         }
     } else if (warp >= 4) {
-        const int ew = warp & 3;
-        const int row = ew * 32 + (int)lane;
+        const int ew = warp & 3;                       // TMEM lane quarter = 32 output channels
+        const int h = (warp - 4) >> 2;                 // pixel half: tile rows 8h .. 8h+7 = accumulator columns 128h ..
+        const int cbase = ew * 32, ch = cbase + static_cast<int>(lane);
         const bool do_stats = p.stat_sum != nullptr;
+        const float bias = (p.bias && ch < p.cout) ? __ldg(p.bias + ch) : 0.f;
+        uint8_t* stage = s_stage + (warp - 4) * 2048;
+        float s1 = 0.f, s2 = 0.f;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -533,19 +607,22 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const int n = tile / (p.tiles_x * p.tiles_y);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            {
-                const int h = (warp - 4) >> 2;            // accumulator half this warp drains
-                const int x = tx * 16 + (row & 15);
-                const int y = ty * 16 + 8 * h + (row >> 4);
-                const bool valid = (x < p.W) && (y < p.H);
-                const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * 128;
-                if (p.dbg != 1) epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * 128;
+            if (p.dbg != 1) {
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b)
+                    epilogue_block_t(p, &tmap_o, taddr + b * 32, cbase, lane, n, tx * 16, ty * 16 + 8 * h + 2 * b, stage,
+                                     bias, do_stats, s1, s2);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
         }
-        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 256, reinterpret_cast<int*>(tmem_slot + 1));
+        if (lane == 0) bulk_wait_group<0>();           // all output tiles written before the CTA retires
+        if (do_stats) {
+            atomicAdd(&s_stat[ch], s1);
+            atomicAdd(&s_stat[BLOCK_N + ch], s2);
+            flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 256, reinterpret_cast<int*>(tmem_slot + 1));
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -553,189 +630,26 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2) of the halo kernel. The halo kernel is limited by the shared-memory operand port:
-// an SS-mode M=128 N=128 K=16 MMA re-reads 4 KB of A and 4 KB of B per 64 cycles (= the 128 B/clk port), and the TMA
-// fill traffic shares that port. Here two CTAs of a cluster cooperate on one 16x16-pixel tile (M = 256):
-//   * each CTA owns 8 tile rows: its activation box is 10 rows x 16 columns per dx (20 KB instead of 36 KB);
-//   * each CTA holds HALF of the output channels of ALL 9 x chunks weight tiles, loaded once and kept resident
-//     (147 KB for cin = 128) - weights are never re-streamed and each SM reads only N/2 rows of B per MMA;
-//   * the leader CTA's MMA thread issues tcgen05.mma.cta_group::2 (M=256, N=128); accumulators live in both CTAs' TMEM;
-//   * TMA completions of both CTAs are signalled on the leader's mbarriers, tcgen05.commit multicasts the
-//     "stage free" / "accumulator ready" arrivals to both CTAs, epilogue warps of both CTAs release the accumulator
-//     on the leader's barrier.
-constexpr int kPARows = 10 * 16;
-constexpr int kPABytes = kPARows * 128;   // 20,480
-constexpr int kPAStages = 3;
-constexpr int kPBTile = 64 * 128;         // one (tap, chunk) half-tile: 64 output channels x 64 k
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w64,
-                       const ConvParams p) {
-    constexpr int BLOCK_N = 128;
-    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0, 256);
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_tiles = 9 * p.cin_chunks;
-    uint8_t* smem_b = smem;                               // resident weights: b_tiles x 8 KB
-    uint8_t* smem_a = smem + 18 * kPBTile;                // activation ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kPAStages * kPABytes);
-    uint64_t* a_full = bars;                              // leader's are used (count 2: one arrive per CTA + tx bytes)
-    uint64_t* a_empty = a_full + kPAStages;               // local, arrived by the multicast commit
-    uint64_t* b_full = a_empty + kPAStages;               // leader's is used
-    uint64_t* tmem_full = b_full + 1;                     // local, multicast commit
-    uint64_t* tmem_empty = tmem_full + 2;                 // leader's are used (count 2 x 128)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BLOCK_N) + 15) & ~uintptr_t(15));   // [4 epilogue warps][2 KB]
-
-    const int warp = threadIdx.x >> 5;
-    const uint32_t lane = lane_id();
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-
-    if (warp == 0 && elect_one()) {
-        tma_prefetch_desc(&tmap_x);
-        tma_prefetch_desc(&tmap_w64);
-    }
-    if (warp == 1 && elect_one()) {
-        for (int i = 0; i < kPAStages; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
-        mbar_init(b_full, 2);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
-        fence_mbar_init();
-    }
-    if (threadIdx.x < 2 * BLOCK_N) s_stat[threadIdx.x] = 0.f;
-    cluster_sync();                                       // barriers of both CTAs initialised before any remote use
-    if (warp == 2) tmem_alloc_2sm(tmem_slot, 256);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            // resident weights: this CTA's 64 output channels of every (tap, chunk) tile
-            const uint32_t bfull0 = mapa_u32(smem_u32(b_full), 0);
-            if (leader) mbar_arrive_expect_tx(b_full, 2u * b_tiles * kPBTile);
-            else mbar_arrive_cluster(bfull0);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int ck = 0; ck < p.cin_chunks; ++ck)
-                    tma_load_3d_2sm(smem_b + (tap * p.cin_chunks + ck) * kPBTile, &tmap_w64, bfull0, ck * 64,
-                                    64 * static_cast<int>(rank), tap);
-            uint32_t sa = 0, pa = 0;
-            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
-                const int tx = tile % p.tiles_x;
-                const int ty = (tile / p.tiles_x) % p.tiles_y;
-                const int n = tile / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * 16, y0 = ty * 16 + 8 * static_cast<int>(rank);
-                for (int dx = 0; dx < 3; ++dx) {
-                    for (int ck = 0; ck < p.cin_chunks; ++ck) {
-                        mbar_wait(&a_empty[sa], pa ^ 1);
-                        const uint32_t afull0 = mapa_u32(smem_u32(&a_full[sa]), 0);
-                        if (leader) mbar_arrive_expect_tx(&a_full[sa], 2u * kPABytes);
-                        else mbar_arrive_cluster(afull0);
-                        tma_load_4d_2sm(smem_a + sa * kPABytes, &tmap_x, afull0, ck * 64, x0 + dx - 1, y0 - 1, n);
-                        if (++sa == kPAStages) { sa = 0; pa ^= 1; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1 && leader) {
-        uint32_t sa = 0, pa = 0, it = 0;
-        mbar_wait(b_full, 0);
-        tc_fence_after();
-        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 128;
-            bool first = true;
-            for (int dx = 0; dx < 3; ++dx) {
-                for (int ck = 0; ck < p.cin_chunks; ++ck) {
-                    mbar_wait(&a_full[sa], pa);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_addr = smem_u32(smem_a + sa * kPABytes);
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint64_t adesc = umma_smem_desc_sw128(a_addr + dy * 2048, 0, 1024);
-                            const uint64_t bdesc = umma_smem_desc_sw128(
-                                smem_u32(smem_b + ((dy * 3 + dx) * p.cin_chunks + ck) * kPBTile), 0, 1024);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc,
-                                              (first && dy == 0 && k == 0) ? 0u : 1u);
-                        }
-                        umma_commit_2sm(&a_empty[sa], 3);
-                    }
-                    __syncwarp();
-                    first = false;
-                    if (++sa == kPAStages) { sa = 0; pa ^= 1; }
-                }
-            }
-            if (elect_one()) umma_commit_2sm(&tmem_full[acc], 3);
-            __syncwarp();
-        }
-    } else if (warp >= 4) {
-        const int ew = warp & 3;
-        const int row = ew * 32 + (int)lane;
-        const bool do_stats = p.stat_sum != nullptr;
-        uint32_t it = 0;
-        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int tx = tile % p.tiles_x;
-            const int ty = (tile / p.tiles_x) % p.tiles_y;
-            const int n = tile / (p.tiles_x * p.tiles_y);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const int x = tx * 16 + (row & 15);
-            const int y = ty * 16 + 8 * static_cast<int>(rank) + (row >> 4);
-            const bool valid = (x < p.W) && (y < p.H);
-            const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 128;
-            epilogue_rows<BLOCK_N>(p, taddr, valid, pix, lane, s_stat, do_stats, s_stage + (warp - 4) * 2048);
-            tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
-        }
-        if (do_stats) flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 128, reinterpret_cast<int*>(tmem_slot + 1));
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();                                       // nobody exits while the peer may still signal its barriers
-    tc_fence_after();
-    if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
-}
-
 static int g_conv_debug = 0;
-static bool g_pair_default = false;   // the CTA-pair kernel is correct but measured slower than the halo kernel (profiles/README.md)
-static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible, 3 CTA-pair whenever eligible
-
-static int launch_conv_pair(const CUtensorMap& tx, const CUtensorMap& tw64, const ConvParams& p, cudaStream_t stream) {
-    constexpr int smem_bytes = 18 * kPBTile + kPAStages * kPABytes + 1024 + 256 + 2 * 128 * 4 + 4 * 2048;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr_set = true;
-    }
-    int clusters = sm_count() / 2;
-    if (p.num_tiles < clusters) clusters = p.num_tiles;
-    conv_igemm_pair_kernel<<<2 * clusters, kThreads, smem_bytes, stream>>>(tx, tw64, p);
-    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
-    return HD_OK;
-}
+static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible
 
 static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-    constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 8 * 2048;
+    constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 128 + 8 * 2048;
     static bool attr_set = false;
     if (!attr_set) {
         HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            smem_bytes));
         attr_set = true;
     }
+    // store box of the transposed epilogue: 32 channels x 16 columns x 2 rows, dense (un-swizzled) in shared memory
+    alignas(64) CUtensorMap to;
+    uint64_t dims[4] = {(uint64_t)p.cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    uint64_t str[3] = {(uint64_t)p.out_cs * 2, (uint64_t)p.W * p.out_cs * 2, (uint64_t)p.H * p.W * p.out_cs * 2};
+    uint32_t box[4] = {32, 16, 2, 1};
+    int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle128=*/false);
+    if (rc) return rc;
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_igemm_halo_kernel<<<grid, kHaloThreads, smem_bytes, stream>>>(tx, tw, p);
+    conv_igemm_halo_kernel<<<grid, kHaloThreads, smem_bytes, stream>>>(tx, tw, to, p);
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -802,13 +716,12 @@ extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out
     }
 
     // halo variant: 3x3, 128 output channels, map >= 16x16 and enough 16x16 tiles to fill the machine
-    bool halo = false, pair = false;
-    if (ksize == 3 && block_n == 128 && H >= 16 && W >= 16 && out_mode == 0 && g_conv_variant != 1) {
+    bool halo = false;
+    if (ksize == 3 && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 && g_conv_variant != 1) {
         const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
-        pair = g_conv_variant == 3 || (g_conv_variant == 0 && g_pair_default && ht >= sm_count());
-        halo = !pair && (g_conv_variant == 2 || ht >= sm_count());
-        if (halo || pair) {
-            tw = 16; th = pair ? 10 : 18; tn = 1;
+        halo = g_conv_variant == 2 || ht >= sm_count();
+        if (halo) {
+            tw = 16; th = 18; tn = 1;
             p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
             p.num_tiles = ht;
         }
@@ -827,15 +740,6 @@ extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out
         uint32_t box[3] = {64, (uint32_t)block_n, 1};
         int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);
         if (rc) return rc;
-    }
-    if (pair) {
-        alignas(64) CUtensorMap tmw64;
-        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)block_n, (uint64_t)(ksize * ksize)};
-        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)block_n * cin * 2};
-        uint32_t box[3] = {64, 64, 1};
-        int rc = make_tmap_bf16(&tmw64, w_packed, 3, dims, str, box);
-        if (rc) return rc;
-        return launch_conv_pair(tmx, tmw64, p, stream);
     }
     if (halo) return launch_conv_halo(tmx, tmw, p, stream);
     if (block_n == 128) return launch_conv<128>(tmx, tmw, p, stream);

@@ -37,7 +37,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box) {
+                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     cuuint64_t gdim[5];
@@ -51,7 +51,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
-                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(HD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",

@@ -204,10 +204,49 @@ def golden_encode(ref_tf):
     print("encode KAT", res["kat_heat"], res["kat_off"], res["kat_wh"], res["kat_box"])
 
 
+def encode_f32_cases():
+    """Box lists with float32-representable coordinates (what the device encoder takes) covering: ordinary boxes,
+    boxes clipped by every border, two boxes sharing a centre cell (the later one owns offset/size), concentric
+    same-class boxes (running maximum), an empty image, a `None` slot, both classes. 256x256 input -> 64x64 maps."""
+    rs = np.random.RandomState(20260921)
+    imgs = []
+    for b in range(5):
+        boxes, labels = [], []
+        for _ in range(rs.randint(1, 7)):
+            x0, y0 = rs.uniform(0, 0.8 * 256, 2)
+            bw, bh = rs.uniform(0.04, 0.5, 2) * 256
+            boxes.append([float(np.float32(v)) for v in (x0, y0, min(x0 + bw, 255.0), min(y0 + bh, 255.0))])
+            labels.append(int(rs.randint(0, 2)))
+        imgs.append((boxes, labels))
+    imgs.append(([[0.0, 0.0, 37.5, 21.25], [200.5, 0.0, 255.0, 90.0], [0.0, 180.0, 60.0, 255.75], [190.0, 170.0, 255.0, 255.0]],
+                 [0, 1, 0, 1]))                                                     # clipped by each border / corner
+    imgs.append(([[100.0, 100.0, 140.0, 140.0], [110.0, 110.0, 130.5, 131.0], [90.0, 80.0, 150.0, 160.0]], [1, 1, 1]))
+    imgs.append(([[64.0, 64.0, 96.0, 96.0], None, [66.0, 62.0, 94.5, 98.0]], [0, 1, 1]))   # same centre cell, None slot
+    imgs.append(([], []))                                                           # no boxes
+    return imgs
+
+
+def golden_encode_f32(ref_tf):
+    res = {}
+    for normalized in (False, True):
+        outs = [[], [], [], []]
+        for boxes, labels in encode_f32_cases():
+            for lst, arr in zip(outs, ref_tf.box2hm(boxes, labels, (256, 256), normalized=normalized)):
+                lst.append(arr)
+        tag = "norm" if normalized else "raw"
+        for name, o in zip(("heat", "off", "size", "mask"), outs):
+            res[f"{tag}_{name}"] = np.stack(o)
+    np.savez_compressed(os.path.join(HERE, "encode_f32.npz"), **res)
+    print("encode_f32", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref_hg, ref_loss, ref_tf, ref_ev = import_reference()
     golden_encode(ref_tf)
+    golden_encode_f32(ref_tf)
+    if os.environ.get("HD_GOLDEN_ONLY") == "encode":
+        sys.exit(0)
     golden_decode(ref_tf, ref_ev)
     golden_loss(ref_loss, ref_tf)
     golden_hourglass(ref_hg, ref_loss, ref_tf)

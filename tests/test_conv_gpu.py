@@ -125,10 +125,11 @@ HALO_CASES = [(2, 32, 32, 128, 128, 3), (1, 64, 48, 128, 128, 3), (1, 40, 24, 12
               (3, 17, 33, 128, 128, 3)]
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2])
 @pytest.mark.parametrize("N,H,W,cin,cout,k", HALO_CASES)
 def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k, variant):
-    """The halo-reuse M=256 kernel (variant 2) and its CTA-pair / cta_group::2 version (variant 3), forced, must agree
+    """The halo kernel (transposed product: M = 128 channels, N = 256 pixels, TMA-store epilogue), forced onto shapes
+    the dispatcher would give to the generic kernel too (ragged 17x33 / 40x24 maps, cin = 64), must agree
     with PyTorch exactly like the generic kernel: forward with bias, residual addend and BN statistics, and dgrad."""
     from real_time_helmet_detection_b200 import ops, _lib
     g = torch.Generator().manual_seed(77 + H + W)

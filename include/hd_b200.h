@@ -65,11 +65,23 @@ int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out
                        int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                        const hd_bn_fuse* bn, hd_stream_t stream);
 
+/* Same convolution with a per-channel affine (+ residual addend) (+ ReLU) epilogue - the eval-mode `Convolution`
+ * (hourglass.py:105-108 with BatchNorm on running statistics) and the `Residual` tail (hourglass.py:123-127) in ONE
+ * launch:  out = relu?( (conv + bias) * scale[c] + shift[c] + addend ),  NHWC bf16 output with channel stride out_cs.
+ * scale / shift: fp32 [cout] or both NULL; block_n 128 or 64. */
+int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void* out, const float* bias, const void* addend,
+                           const float* scale, const float* shift, int relu, int N, int H, int W, int cin, int cout,
+                           int block_n, int ksize, int out_cs, hd_stream_t stream);
+/* Eval-mode BatchNorm folded to scale / shift for a whole table of layers in one launch. jobs_host: njobs records
+ * {const float* gamma, beta, running_mean, running_var; float* out; int channels; float eps} (out[0..C) = scale =
+ * gamma * rsqrt(var + eps), out[C..2C) = shift = beta - mean * scale); jobs_dev: device scratch of the same size. */
+int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, hd_stream_t stream);
+
 /* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the
- * halo-reuse M=256 kernel (3x3, block_n 128, map >= 16x16) whenever the shape is eligible. */
+ * halo kernel (3x3, 128 output channels, map >= 16x16) whenever the shape is eligible. */
 void hd_set_conv_variant(int variant);
 /* Profiling only (results are wrong when non-zero): 1 = epilogue drains TMEM but skips math/stores, 2 = MMA issue
- * skipped, 3 = weight tiles loaded only for a CTA's first tile (halo kernel). */
+ * skipped (halo kernel). */
 void hd_set_conv_debug(int mode);
 
 /* Weight gradient of the same convs (autograd of hourglass.py:100): grad_w (OIHW fp32 [cout][cin_real][k][k])

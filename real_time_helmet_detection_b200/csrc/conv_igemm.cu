@@ -50,6 +50,9 @@ struct ConvParams {
     // optional fused train-mode BN finalize by the last CTA to flush its statistics (see hd_bn_fuse in hd_b200.h)
     const float* bn_gamma; const float* bn_beta; float* bn_rm; float* bn_rv; long long* bn_nbt;
     float bn_momentum, bn_eps, bn_count; float* bn_out; unsigned int* bn_counter;
+    // optional per-channel affine + ReLU epilogue (eval-mode BatchNorm folded into the conv, hd_conv2d_igemm_affine):
+    // out = relu?( (conv + bias) * ep_scale[c] + ep_shift[c] + addend )
+    const float* ep_scale; const float* ep_shift; int ep_relu;
     int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
                               // 2 = MMA issue skipped (halo kernel only)
 };
@@ -90,6 +93,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
         }
+        if (p.ep_scale) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], __ldg(p.ep_scale + c0 + i), __ldg(p.ep_shift + c0 + i));
+        }
         if (p.addend) {
             // coalesced read of the 32 rows x 64 B addend tile through the staging buffer (8 rows x 64 B per
             // instruction), then every lane picks up its own row
@@ -117,6 +124,10 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t tadd
                 }
             }
             __syncwarp();
+        }
+        if (p.ep_relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         {
             const uint32_t swz = (lane >> 1) & 3u;
@@ -429,7 +440,7 @@ constexpr int kHaloThreads = 384;
 // = 2048 of the tile's 9216 MMA cycles), which the tensor core's own accumulator traffic has to share.
 __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUtensorMap* tmap_o, uint32_t taddr, int cbase,
                                                  uint32_t lane, int n, int x0, int yb, uint8_t* stage, float bias,
-                                                 bool do_stats, float& s1, float& s2) {
+                                                 float ep_scale, float ep_shift, bool do_stats, float& s1, float& s2) {
     uint32_t r[32];
     tmem_ld_x32(taddr, r);
     // Lane pair (2m, 2m+1) = channels (c, c+1). For the pixel pair (2j, 2j+1) the even lane ends up with both channels
@@ -450,7 +461,7 @@ __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUte
     tmem_ld_wait();
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias;
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]) + bias, ep_scale, ep_shift);
     if (p.addend) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -461,6 +472,10 @@ __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUte
             v[2 * j] += __uint_as_float(odd ? (w0 & 0xffff0000u) : (w0 << 16));
             v[2 * j + 1] += __uint_as_float(odd ? (w1 & 0xffff0000u) : (w1 << 16));
         }
+    }
+    if (p.ep_relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     // the previous TMA store of this warp must have finished reading the staging buffer before it is overwritten
     if (lane == 0) bulk_wait_group_read<0>();
@@ -597,6 +612,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const int cbase = ew * 32, ch = cbase + static_cast<int>(lane);
         const bool do_stats = p.stat_sum != nullptr;
         const float bias = (p.bias && ch < p.cout) ? __ldg(p.bias + ch) : 0.f;
+        const float ep_scale = p.ep_scale ? __ldg(p.ep_scale + ch) : 1.f, ep_shift = p.ep_scale ? __ldg(p.ep_shift + ch) : 0.f;
         uint8_t* stage = s_stage + (warp - 4) * 2048;
         float s1 = 0.f, s2 = 0.f;
         uint32_t it = 0;
@@ -612,7 +628,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 #pragma unroll 1
                 for (int b = 0; b < 4; ++b)
                     epilogue_block_t(p, &tmap_o, taddr + b * 32, cbase, lane, n, tx * 16, ty * 16 + 8 * h + 2 * b, stage,
-                                     bias, do_stats, s1, s2);
+                                     bias, ep_scale, ep_shift, do_stats, s1, s2);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -661,24 +677,45 @@ extern "C" void hd_set_conv_variant(int v) { hd::g_conv_variant = v; }
 // Profiling only: see ConvParams::dbg (results are wrong when non-zero).
 extern "C" void hd_set_conv_debug(int v) { hd::g_conv_debug = v; }
 
-extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
-                                  const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
-                                  int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs,
-                                  int stack_idx, int num_stack, const hd_bn_fuse* bn, cudaStream_t stream);
+static int conv_dispatch(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                         const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
+                         int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
+                         const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
+                         cudaStream_t stream);
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
                                const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
                                int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx,
                                int num_stack, cudaStream_t stream) {
-    return hd_conv2d_igemm_bn(x, w_packed, out, out2, bias, addend, stat_sum, stat_sqsum, N, H, W, cin, cout, block_n,
-                              ksize, out_mode, out_cs, out2_cs, stack_idx, num_stack, nullptr, stream);
+    return conv_dispatch(x, w_packed, out, out2, bias, addend, stat_sum, stat_sqsum, N, H, W, cin, cout, block_n, ksize,
+                         out_mode, out_cs, out2_cs, stack_idx, num_stack, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
                                   const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin,
                                   int cout, int block_n, int ksize, int out_mode, int out_cs, int out2_cs,
                                   int stack_idx, int num_stack, const hd_bn_fuse* bn, cudaStream_t stream) {
+    return conv_dispatch(x, w_packed, out, out2, bias, addend, stat_sum, stat_sqsum, N, H, W, cin, cout, block_n, ksize,
+                         out_mode, out_cs, out2_cs, stack_idx, num_stack, bn, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void* out, const float* bias,
+                                      const void* addend, const float* scale, const float* shift, int relu, int N,
+                                      int H, int W, int cin, int cout, int block_n, int ksize, int out_cs,
+                                      cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE((scale == nullptr) == (shift == nullptr), "conv_igemm_affine: scale and shift come together");
+    HD_REQUIRE(block_n == 128 || block_n == 64, "conv_igemm_affine: block_n=%d unsupported", block_n);
+    return conv_dispatch(x, w_packed, out, nullptr, bias, addend, nullptr, nullptr, N, H, W, cin, cout, block_n, ksize, 0,
+                         out_cs, 0, 0, 1, nullptr, scale, shift, relu, stream);
+}
+
+static int conv_dispatch(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
+                         const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
+                         int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
+                         const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
+                         cudaStream_t stream) {
     using namespace hd;
     HD_REQUIRE(bn == nullptr || (stat_sum != nullptr && bn->out && bn->counter && bn->gamma && bn->beta),
                "conv_igemm: fused BN finalize needs statistics, gamma/beta, an output block and a ticket counter");
@@ -709,6 +746,7 @@ extern "C" int hd_conv2d_igemm_bn(const void* x, const void* w_packed, void* out
     p.bias = bias; p.addend = reinterpret_cast<const __nv_bfloat16*>(addend);
     p.stat_sum = stat_sum; p.stat_sqsum = stat_sqsum;
     p.dbg = g_conv_debug;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.ep_relu = ep_relu;
     if (bn) {
         p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_rm = bn->running_mean; p.bn_rv = bn->running_var;
         p.bn_nbt = bn->num_batches_tracked; p.bn_momentum = bn->momentum; p.bn_eps = bn->eps;

@@ -665,3 +665,30 @@ extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaS
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ eval-mode BN fold
+namespace hd {
+struct BnFoldJob {
+    const float* gamma; const float* beta; const float* mean; const float* var;
+    float* out; int channels; float eps;
+};
+__global__ void bn_fold_all_kernel(const BnFoldJob* __restrict__ jobs) {
+    const BnFoldJob j = jobs[blockIdx.x];
+    for (int c = threadIdx.x; c < j.channels; c += blockDim.x) {
+        const float sc = j.gamma[c] * rsqrtf(j.var[c] + j.eps);
+        j.out[c] = sc;
+        j.out[j.channels + c] = j.beta[c] - j.mean[c] * sc;
+    }
+}
+}  // namespace hd
+
+extern "C" int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(njobs > 0 && jobs_host && jobs_dev, "bn_fold_all: empty job table");
+    // small pageable -> device copy, stream-ordered (the runtime stages the source before returning)
+    HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(BnFoldJob),
+                                  cudaMemcpyHostToDevice, stream));
+    bn_fold_all_kernel<<<njobs, 128, 0, stream>>>(reinterpret_cast<const BnFoldJob*>(jobs_dev));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}

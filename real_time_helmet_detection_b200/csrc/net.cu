@@ -97,6 +97,7 @@ struct hd_net {
     size_t wgrad_ws_bytes = 0;
     float* small = nullptr;   // scratch for BN-backward sums / coefficients
     void* pack_jobs_dev = nullptr;          // device copy of the weight-pack job table
+    void* fold_jobs_dev = nullptr;          // device copy of the eval-mode BN fold table
     unsigned int* tickets = nullptr;        // one zeroed word per unit: "last CTA finalizes the BN" ticket counters
     // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
     // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
@@ -218,6 +219,7 @@ static void plan_persistent(hd_net* n) {
     n->small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->alt.small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->pack_jobs_dev = a.alloc(2 * n->units.size() * 64);
+    n->fold_jobs_dev = a.alloc(n->units.size() * 64);
     n->persist_bytes = (stats_total + n->units.size()) * sizeof(float);
 }
 
@@ -261,6 +263,24 @@ static void pack_weights(hd_net* n, bool need_dgrad) {
     RUN(hd_pack_all_weights(n->pack_jobs_dev, static_cast<int>(jobs.size()), total, n->stream));
 }
 
+// Eval mode: every BatchNorm (running statistics) is folded to scale / shift once per forward, in ONE launch; the
+// convolutions then apply it (+ residual addend, + ReLU) in their epilogue (hd_conv2d_igemm_affine), so a `Convolution`
+// is one launch instead of conv + finalize + bn_act and the eval forward has ~50 launches instead of ~125.
+struct BnFoldJobHost {
+    const float* gamma; const float* beta; const float* mean; const float* var;
+    float* out; int channels; float eps;
+};
+static void fold_bn(hd_net* n) {
+    std::vector<BnFoldJobHost> jobs;
+    for (size_t i = 0; i < n->units.size(); ++i) {
+        Unit& u = n->units[i];
+        if (!u.bn) continue;
+        const hd_unit_ptrs& p = UP(n, static_cast<int>(i));
+        jobs.push_back(BnFoldJobHost{p.gamma, p.beta, p.running_mean, p.running_var, u.bnp, u.cout, 1e-5f});
+    }
+    if (!jobs.empty()) RUN(hd_bn_fold_all(jobs.data(), static_cast<int>(jobs.size()), n->fold_jobs_dev, n->stream));
+}
+
 static cudaEvent_t next_event(hd_net* n) {
     if (n->events.empty()) {
         n->events.resize(128);
@@ -294,7 +314,10 @@ static void swap_lane(hd_net* n) {
 }
 
 // conv (+ bias) -> raw output + BN statistics; then finalize the BN of this unit
-static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, int W, const bf16* addend, int training) {
+// training: y = raw conv output (+ bias, + addend), BN statistics / finalize fused; the caller applies the BN.
+// eval, BN layer: y = relu?(bn(conv) + addend) in one launch (the caller must NOT apply the BN again).
+static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, int W, const bf16* addend, int training,
+                      int eval_relu = 0) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
     const int cin_gemm = u.kind == 1 ? 192 : pad64(u.cin);
@@ -311,12 +334,13 @@ static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, i
                                cin_gemm, u.cout, block_n_for(u.cout), k, 0, u.cout, 0, 0, 1, &bn, n->stream));
         return;
     }
+    if (u.bn) {
+        RUN(hd_conv2d_igemm_affine(x, u.wp, y, u.bias ? p.b : nullptr, addend, u.bnp, u.bnp + u.cout, eval_relu, B, H, W,
+                                   cin_gemm, u.cout, block_n_for(u.cout), k, u.cout, n->stream));
+        return;
+    }
     RUN(hd_conv2d_igemm(x, u.wp, y, nullptr, u.bias ? p.b : nullptr, addend, nullptr, nullptr, B, H, W, cin_gemm, u.cout,
                         block_n_for(u.cout), k, 0, u.cout, 0, 0, 1, n->stream));
-    if (u.bn)
-        RUN(hd_bn_finalize(u.stats, u.stats + u.cout, static_cast<float>(u.npix), p.gamma, p.beta, p.running_mean,
-                           p.running_var, p.num_batches_tracked, 0.1f, 1e-5f, training, u.bnp, u.bnp + u.cout,
-                           u.bnp + 2 * u.cout, u.bnp + 3 * u.cout, u.cout, n->stream));
 }
 
 static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int training) {
@@ -330,6 +354,17 @@ static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int t
     r.Ys = r.us >= 0 ? reinterpret_cast<bf16*>(n->fw.alloc(bytes)) : nullptr;
     r.Out = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
     Unit &u1 = n->units[r.u1], &u2 = n->units[r.u2];
+    if (!training) {
+        // relu(bn1(conv1)) -> Z1 ; [bn_s(conv_s) -> Ys] ; relu(bn2(conv2) + skip) -> Out : 2-3 launches
+        conv_unit(n, r.u1, X, r.Z1, B, H, W, nullptr, 0, 1);
+        const bf16* skip = X;
+        if (r.us >= 0) {
+            conv_unit(n, r.us, X, r.Ys, B, H, W, nullptr, 0, 0);
+            skip = r.Ys;
+        }
+        conv_unit(n, r.u2, r.Z1, r.Out, B, H, W, skip, 0, 1);
+        return r.Out;
+    }
     conv_unit(n, r.u1, X, r.Y1, B, H, W, nullptr, training);
     RUN(hd_bn_act(r.Y1, u1.bnp, u1.bnp + u1.cout, r.Z1, npix, r.cout, 1, n->stream));
     conv_unit(n, r.u2, r.Z1, r.Y2, B, H, W, nullptr, training);
@@ -377,6 +412,7 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
                            cudaMemsetAsync(n->alt.small, 0, 16 * 256 * sizeof(float), n->stream) != cudaSuccess))
             n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN-backward scratch failed");
         pack_weights(n, training != 0);
+        if (!training) fold_bn(n);
     }
     // ---- PreLayer (hourglass.py:159-173)
     Unit& u0 = n->units[0];
@@ -384,8 +420,12 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     n->Y0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
     n->Z0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
     RUN(hd_stem_im2col(x, n->patches, B, H, W, n->stream));
-    conv_unit(n, 0, n->patches, n->Y0, B, H2, W2, nullptr, training);
-    RUN(hd_bn_act(n->Y0, u0.bnp, u0.bnp + 64, n->Z0, static_cast<long long>(B) * H2 * W2, 64, 1, n->stream));
+    if (training) {
+        conv_unit(n, 0, n->patches, n->Y0, B, H2, W2, nullptr, training);
+        RUN(hd_bn_act(n->Y0, u0.bnp, u0.bnp + 64, n->Z0, static_cast<long long>(B) * H2 * W2, 64, 1, n->stream));
+    } else {
+        conv_unit(n, 0, n->patches, n->Z0, B, H2, W2, nullptr, 0, 1);
+    }
     bf16* r1 = residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training);
     n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
     RUN(hd_maxpool2(r1, n->R1pool, B, H2, W2, 128, n->stream));
@@ -400,8 +440,12 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
         Unit& un = n->units[s.u_neck];
         s.Yn = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
         s.F1 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
-        conv_unit(n, s.u_neck, s.hg_out, s.Yn, B, H4, W4, nullptr, training);
-        RUN(hd_bn_act(s.Yn, un.bnp, un.bnp + C, s.F1, npix4, C, 1, n->stream));
+        if (training) {
+            conv_unit(n, s.u_neck, s.hg_out, s.Yn, B, H4, W4, nullptr, training);
+            RUN(hd_bn_act(s.Yn, un.bnp, un.bnp + C, s.F1, npix4, C, 1, n->stream));
+        } else {
+            conv_unit(n, s.u_neck, s.hg_out, s.F1, B, H4, W4, nullptr, 0, 1);
+        }
         s.F2 = residual_fwd(n, s.neck_res, s.F1, B, H4, W4, training);
         Unit& uh = n->units[s.u_head];
         const bool merge = i < n->S - 1;

@@ -82,6 +82,22 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, cout: int, ksize: int,
     return out_t
 
 
+def conv2d_igemm_affine(x: torch.Tensor, w_packed: torch.Tensor, cout: int, ksize: int, scale: torch.Tensor | None,
+                        shift: torch.Tensor | None, relu: bool, bias: torch.Tensor | None = None,
+                        addend: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Eval-mode `Convolution` / `Residual` tail in one launch: relu?((conv + bias) * scale + shift + addend), NHWC bf16."""
+    _lib.require_cuda(x, "x")
+    n, h, w, cin = x.shape
+    block_n = w_packed.shape[1]
+    assert w_packed.shape[2] == cin and w_packed.shape[0] == ksize * ksize
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    check(_lib.lib().hd_conv2d_igemm_affine(ptr(x), ptr(w_packed), ptr(out), ptr(bias), ptr(addend), ptr(scale), ptr(shift),
+                                            1 if relu else 0, n, h, w, cin, cout, block_n, ksize, out.shape[3], stream()),
+          "conv2d_igemm_affine")
+    return out
+
+
 def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, cin_real: int, ksize: int, grad: torch.Tensor | None = None,
                  accumulate: bool = False, stem_perm: bool = False) -> torch.Tensor:
     """x: NHWC bf16 [N,H,W,cin], dy: NHWC bf16 [N,H,W,128] -> grad OIHW fp32 [128, cin_real, k, k]."""

@@ -159,3 +159,60 @@ def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k, variant):
     assert torch.allclose(stats[1].cpu(), s2, rtol=1e-3)
     if cin == cout:
         assert _rel_l2(dx, dref) <= 3e-3
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,relu,with_add", [
+    (2, 32, 32, 128, 128, 3, True, True),      # halo kernel (forced below) and generic kernel
+    (1, 40, 24, 128, 128, 3, False, True),
+    (2, 16, 16, 64, 128, 1, False, False),     # skip conv 1x1 64->128
+    (3, 8, 8, 128, 128, 3, True, False),
+    (1, 32, 32, 192, 64, 1, True, False),      # stem GEMM shape (K = 192, 64 channels)
+])
+def test_conv_affine_epilogue(cuda_device, N, H, W, cin, cout, k, relu, with_add):
+    """hd_conv2d_igemm_affine: eval-mode Convolution (BN folded to scale/shift) + residual addend + ReLU in the conv
+    epilogue == relu((conv + bias) * scale + shift + addend) of PyTorch, on the generic and the halo kernel."""
+    from real_time_helmet_detection_b200 import ops, _lib
+    g = torch.Generator().manual_seed(5 + H + cin)
+    x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
+    w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    bias = torch.randn(cout, generator=g)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    r = _bf16_round(torch.randn(N, cout, H, W, generator=g)) if with_add else None
+    ref = (F.conv2d(x, w, bias, padding=(k - 1) // 2)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if with_add:
+        ref = ref + r
+    if relu:
+        ref = torch.relu(ref)
+    rows = 128 if cout == 128 else 64
+    wp = ops.pack_weight(w.to(cuda_device), rows_pad=rows) if cout != 128 else ops.pack_weight(w.to(cuda_device))
+    for variant in ((1, 2) if (k == 3 and H >= 16 and cout == 128) else (0,)):
+        _lib.lib().hd_set_conv_variant(variant)
+        try:
+            y = ops.conv2d_igemm_affine(ops.to_nhwc(x.to(cuda_device)), wp, cout, k, scale.to(cuda_device),
+                                        shift.to(cuda_device), relu, bias=bias.to(cuda_device),
+                                        addend=ops.to_nhwc(r.to(cuda_device)) if with_add else None)
+        finally:
+            _lib.lib().hd_set_conv_variant(0)
+        out = ops.to_nchw(y).cpu()
+        assert _rel_l2(out, ref) <= 3e-3, (variant, _rel_l2(out, ref))
+        assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-2
+
+
+def test_bn_fold_all(cuda_device):
+    import ctypes
+    from real_time_helmet_detection_b200 import _lib
+    class Job(ctypes.Structure):
+        _fields_ = [("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("mean", ctypes.c_void_p),
+                    ("var", ctypes.c_void_p), ("out", ctypes.c_void_p), ("channels", ctypes.c_int), ("eps", ctypes.c_float)]
+    g = torch.Generator().manual_seed(1)
+    chans = [64, 128, 128, 6]
+    ts = [[torch.randn(c, generator=g).to(cuda_device) for _ in range(3)] + [(torch.rand(c, generator=g) + 0.1).to(cuda_device)]
+          for c in chans]
+    outs = [torch.zeros(2 * c, device=cuda_device) for c in chans]
+    jobs = (Job * len(chans))(*[Job(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), o.data_ptr(), c, 1e-5)
+                                for t, o, c in zip(ts, outs, chans)])
+    dev_jobs = torch.zeros(len(chans) * ctypes.sizeof(Job), dtype=torch.uint8, device=cuda_device)
+    _lib.check(_lib.lib().hd_bn_fold_all(ctypes.cast(jobs, ctypes.c_void_p), len(chans), _lib.ptr(dev_jobs), _lib.stream()))
+    for t, o, c in zip(ts, outs, chans):
+        sc = t[0] * torch.rsqrt(t[3] + 1e-5)
+        assert torch.allclose(o[:c], sc, rtol=1e-6, atol=1e-7) and torch.allclose(o[c:], t[1] - t[2] * sc, rtol=1e-6, atol=1e-6)

@@ -30,6 +30,10 @@ const char* hd_last_error(void);
 int hd_version(void);
 /* Kernels launched by this library in this process so far (instrumentation for bench.py's gpu_launches). */
 long long hd_launch_count(void);
+/* Programmatic dependent launch (every kernel is launched with the programmatic-stream-serialization attribute and
+ * starts with griddepcontrol.launch_dependents / griddepcontrol.wait): 1 = on (default), 0 = off. HD_NO_PDL=1 in the
+ * environment also turns it off. */
+void hd_set_pdl(int on);
 
 /* ------------------------------------------------------------------ convolutions (hourglass.py:94-108) */
 

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "hd_last_error": (c_char_p, []),
     "hd_version": (I, []),
     "hd_launch_count": (LL, []),
+    "hd_set_pdl": (None, [I]),
     "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_igemm_affine": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_bn_fold_all": (I, [P, I, P, P]),

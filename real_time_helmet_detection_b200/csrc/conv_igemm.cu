@@ -215,6 +215,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(BLOCK_N >= 64 ? 384 : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const ConvParams p) {
+    pdl_launch_dependents();
     constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;
     constexpr int kBBytes = BLOCK_N * 128;
     constexpr int kStageBytes = kABytes + kBBytes;
@@ -256,6 +257,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     const int ksteps = p.kh * p.kw * p.cin_chunks;
     const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2;
@@ -400,7 +402,8 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_igemm_kernel<BLOCK_N><<<grid, BLOCK_N >= 64 ? 384 : kThreads, smem_bytes, stream>>>(tx, tw, p);
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_kernel<BLOCK_N>, grid, BLOCK_N >= 64 ? 384 : kThreads,
+                                     smem_bytes, stream, tx, tw, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -508,6 +511,7 @@ __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUte
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
+    pdl_launch_dependents();
     constexpr int BLOCK_N = 128;                                   // output channels (the MMA's M here)
     constexpr uint32_t kIdesc = umma_idesc_bf16(256, 0, 0);        // M = 128 channels, N = 256 pixels
     extern __shared__ uint8_t smem_raw[];
@@ -544,6 +548,7 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         if (elect_one()) {
@@ -665,7 +670,8 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
     int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle128=*/false);
     if (rc) return rc;
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_igemm_halo_kernel<<<grid, kHaloThreads, smem_bytes, stream>>>(tx, tw, to, p);
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes, stream, tx, tw,
+                                     to, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

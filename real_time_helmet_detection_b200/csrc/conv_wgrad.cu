@@ -42,6 +42,7 @@ template <int BLOCK_N, bool HALO>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
+    pdl_launch_dependents();
     constexpr int kBRows = HALO ? 160 : 128;
     constexpr int kBBytes = kBRows * BLOCK_N * 2;
     constexpr int kNChunks = BLOCK_N / 64;
@@ -89,6 +90,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
 
     if (warp == 0) {
         if (elect_one()) {
@@ -224,6 +226,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 // back to the OIHW position [co][c][ky][kx].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int ksplit, int taps,
                                     int cout, int cin, int rows_pad, int cin_pad, int accumulate, int stem_perm) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over taps * cout * cin, ci fastest
     const int total = taps * cout * cin;
     if (idx >= total) return;
@@ -252,7 +255,8 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set = true;
     }
-    conv_wgrad_kernel<BLOCK_N, HALO><<<p.groups * p.ksplit, kWgThreads, smem_bytes, stream>>>(tdy, tx, p);
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HALO>, p.groups * p.ksplit,
+                                     kWgThreads, smem_bytes, stream, tdy, tx, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -325,8 +329,7 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
                             : (halo ? launch_wgrad<64, true>(tdy, tx, p, stream) : launch_wgrad<64, false>(tdy, tx, p, stream));
     if (rc) return rc;
     const int total = p.taps * cout * cin_real;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128,
-                                                                 cin, accumulate, stem_perm);
+    HD_CHECK_CUDA(::hd::launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128, cin, accumulate, stem_perm));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

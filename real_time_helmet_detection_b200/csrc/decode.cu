@@ -56,6 +56,7 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
 // ------------------------------------------------------------------------------------------------ kernel 1
 // grid = (ceil(W/32), ceil(H/8), B*S*C), block = (32, 8): one thread per heat-map element.
 __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
+    pdl_prologue();
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int z = blockIdx.z;
@@ -147,6 +148,7 @@ __device__ __forceinline__ void rank_sort_desc(const unsigned long long* src, un
 }
 
 __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const DecodeArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char dsm[];
     unsigned long long* mat = reinterpret_cast<unsigned long long*>(dsm);             // [kMaxCand][kNmsWords] 128 KB
     unsigned long long* keys = mat + kMaxCand * kNmsWords;                              // [1024] selected
@@ -401,7 +403,7 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     a.out_boxes = out_boxes; a.out_cls = out_cls; a.out_scores = out_scores; a.out_count = out_count;
     HD_CHECK_CUDA(cudaMemsetAsync(a.cand_count, 0, ps * sizeof(int), stream));
     dim3 grid((W + 31) / 32, (H + 7) / 8, static_cast<unsigned>(ps * C));
-    decode_peaks_kernel<<<grid, dim3(32, 8), 0, stream>>>(a);
+    HD_CHECK_CUDA(::hd::launch_k(decode_peaks_kernel, grid, dim3(32, 8), 0, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     static bool attr_set = false;
     if (!attr_set) {
@@ -409,7 +411,7 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
                                            static_cast<int>(kSelSmem)));
         attr_set = true;
     }
-    decode_select_nms_kernel<<<B, kSelThreads, kSelSmem, stream>>>(a);
+    HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, kSelThreads, kSelSmem, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

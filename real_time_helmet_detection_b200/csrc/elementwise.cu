@@ -61,6 +61,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                    int training, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
@@ -90,6 +91,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 template <bool RELU>
 __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                               const float* __restrict__ shift, __nv_bfloat16* __restrict__ z, size_t nvec, int C) {
+    pdl_prologue();
     __shared__ __align__(16) float s_sc[256], s_sh[256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         s_sc[i] = scale[i];
@@ -119,6 +121,7 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
                                    const float* __restrict__ b2, const __nv_bfloat16* __restrict__ skip,
                                    const float* __restrict__ ss, const float* __restrict__ bs,
                                    __nv_bfloat16* __restrict__ out, size_t nvec, int C) {
+    pdl_prologue();
     __shared__ __align__(16) float p[4][256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         p[0][i] = s2[i];
@@ -150,6 +153,7 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
 // 2x2 max pool, stride 2 (H, W even)
 __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                 int W, int C) {
+    pdl_prologue();
     const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -171,6 +175,7 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 // out[n,y,x,:] = up1[n,y,x,:] + low[n,y/2,x/2,:]   (nearest x2 upsample + add); H, W are the OUTPUT sizes
 __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low,
                                     __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+    pdl_prologue();
     const int cvec = C >> 3;
     const size_t nvec = static_cast<size_t>(N) * H * W * cvec;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -201,6 +206,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
                      float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin) {
+    pdl_prologue();
     extern __shared__ __align__(16) float red[];  // [3][C]
     const int cvec = C >> 3;
     const int lane_c = threadIdx.x % cvec;          // which 8-channel vector
@@ -305,6 +311,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, int C) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float g = gamma[c], r = rstd[c], m = mean[c];
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const __nv_bfloat1
                                     __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
                                     const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
                                     __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
+    pdl_prologue();
     __shared__ __align__(16) float p[8][256];
     const bool remask = out == nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -385,6 +393,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const __nv_bfloat1
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dpool,
                                     const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
                                     __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+    pdl_prologue();
     const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -431,6 +440,7 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
 // dlow[n,y,x,:] = sum of the 2x2 block of dout (backward of nearest x2 upsample); H, W are dout's sizes
 __global__ void sum2x2_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dlow, int N, int H,
                               int W, int C) {
+    pdl_prologue();
     const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -452,6 +462,7 @@ __global__ void sum2x2_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloa
 // out = a + b (+ c)
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, size_t nvec) {
+    pdl_prologue();
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         F8 x = load8(a + i * 8), y = load8(b + i * 8);
@@ -469,6 +480,7 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 // out[c] (+)= sum over pixels of x[pix, c]   (bias gradients)
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, size_t npix, int C,
                               int cs) {
+    pdl_prologue();
     extern __shared__ float red[];
     const int cvec = C >> 3;
     const int lane_c = threadIdx.x % cvec, row = threadIdx.x / cvec, rows = blockDim.x / cvec;
@@ -509,9 +521,7 @@ extern "C" int hd_bn_finalize(const float* sum, const float* sqsum, float count,
                               float* shift, float* save_mean, float* save_rstd, int C, cudaStream_t stream) {
     HD_REQUIRE(C > 0 && C <= 256, "bn_finalize: C=%d", C);
     HD_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
-                                                          num_batches_tracked, momentum, eps, training, scale, shift,
-                                                          save_mean, save_rstd, C);
+    HD_CHECK_CUDA(::hd::launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, stream, sum, sqsum, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_rstd, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -522,9 +532,9 @@ extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z,
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (relu)
-        bn_act_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z), nvec, C));
     else
-        bn_act_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y), scale, shift, BFW(z), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z), nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -536,9 +546,9 @@ extern "C" int hd_bn_add_relu(cvp y2, const float* s2, const float* b2, cvp skip
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (ss)
-        bn_add_relu_kernel<true><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C));
     else
-        bn_add_relu_kernel<false><<<ew_blocks(nvec), 256, 0, stream>>>(BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -547,7 +557,7 @@ extern "C" int hd_maxpool2(cvp x, void* y, int N, int H, int W, int C, cudaStrea
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
-    maxpool2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BFW(y), N, H, W, C);
+    HD_CHECK_CUDA(::hd::launch_k(maxpool2_kernel, ew_blocks(nvec), 256, 0, stream, BF(x), BFW(y), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -556,7 +566,7 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "upsample2_add: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * H * W * (C / 8);
     if (nvec == 0) return HD_OK;
-    upsample_add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(up1), BF(low), BFW(out), N, H, W, C);
+    HD_CHECK_CUDA(::hd::launch_k(upsample_add_kernel, ew_blocks(nvec), 256, 0, stream, BF(up1), BF(low), BFW(out), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -588,13 +598,13 @@ extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, c
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
     if (ys && out)
-        bn_bwd_reduce_kernel<true, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin));
     else if (ys)
-        bn_bwd_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin));
     else if (out)
-        bn_bwd_reduce_kernel<false, false><<<blocks, 256, smem, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C, fin);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C, fin));
     else
-        bn_bwd_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C, fin);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C, fin));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -603,8 +613,7 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
                                   const float* mean, const float* rstd, float* coef, float* dgamma, float* dbeta,
                                   int accumulate, int C, cudaStream_t stream) {
     HD_REQUIRE(C > 0 && C <= 256, "bn_bwd_finalize: C=%d", C);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(s0, s1, count, gamma, mean, rstd, coef, dgamma, dbeta,
-                                                              accumulate, C);
+    HD_CHECK_CUDA(::hd::launch_k(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, stream, s0, s1, count, gamma, mean, rstd, coef, dgamma, dbeta, accumulate, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -617,13 +626,13 @@ extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, const float* act_scale, const 
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
     if (ys && gout)
-        bn_bwd_apply_kernel<true, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C));
     else if (ys)
-        bn_bwd_apply_kernel<true, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C));
     else if (gout)
-        bn_bwd_apply_kernel<false, true><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C));
     else
-        bn_bwd_apply_kernel<false, false><<<blocks, 256, 0, stream>>>(BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C);
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -633,7 +642,7 @@ extern "C" int hd_maxpool2_bwd(cvp x, cvp dpool, cvp add1, cvp add2, void* dx, i
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
-    maxpool2_bwd_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C);
+    HD_CHECK_CUDA(::hd::launch_k(maxpool2_bwd_kernel, ew_blocks(nvec), 256, 0, stream, BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -642,7 +651,7 @@ extern "C" int hd_sum2x2(cvp dout, void* dlow, int N, int H, int W, int C, cudaS
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "sum2x2: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
-    sum2x2_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(dout), BFW(dlow), N, H, W, C);
+    HD_CHECK_CUDA(::hd::launch_k(sum2x2_kernel, ew_blocks(nvec), 256, 0, stream, BF(dout), BFW(dlow), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -651,7 +660,7 @@ extern "C" int hd_add(cvp a, cvp b, cvp c, void* out, long long nelem, cudaStrea
     HD_REQUIRE(nelem % 8 == 0, "add: nelem %% 8 != 0");
     const size_t nvec = static_cast<size_t>(nelem) / 8;
     if (nvec == 0) return HD_OK;
-    add_kernel<<<ew_blocks(nvec), 256, 0, stream>>>(BF(a), BF(b), BF(c), BFW(out), nvec);
+    HD_CHECK_CUDA(::hd::launch_k(add_kernel, ew_blocks(nvec), 256, 0, stream, BF(a), BF(b), BF(c), BFW(out), nvec));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -661,7 +670,7 @@ extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaS
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
-    colsum_kernel<<<blocks, 256, static_cast<size_t>(C) * sizeof(float), stream>>>(BF(x), out, static_cast<size_t>(npix), C, cs);
+    HD_CHECK_CUDA(::hd::launch_k(colsum_kernel, blocks, 256, static_cast<size_t>(C) * sizeof(float), stream, BF(x), out, static_cast<size_t>(npix), C, cs));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -673,6 +682,7 @@ struct BnFoldJob {
     float* out; int channels; float eps;
 };
 __global__ void bn_fold_all_kernel(const BnFoldJob* __restrict__ jobs) {
+    pdl_prologue();
     const BnFoldJob j = jobs[blockIdx.x];
     for (int c = threadIdx.x; c < j.channels; c += blockDim.x) {
         const float sc = j.gamma[c] * rsqrtf(j.var[c] + j.eps);
@@ -688,7 +698,7 @@ extern "C" int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, 
     // small pageable -> device copy, stream-ordered (the runtime stages the source before returning)
     HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(BnFoldJob),
                                   cudaMemcpyHostToDevice, stream));
-    bn_fold_all_kernel<<<njobs, 128, 0, stream>>>(reinterpret_cast<const BnFoldJob*>(jobs_dev));
+    HD_CHECK_CUDA(::hd::launch_k(bn_fold_all_kernel, njobs, 128, 0, stream, reinterpret_cast<const BnFoldJob*>(jobs_dev)));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256)
 encode_targets_kernel(const float* __restrict__ boxes, const int* __restrict__ labels, int nmax, int h, int w, int ncls,
                       int scale_factor, int normalized, float* __restrict__ heat, float* __restrict__ off,
                       float* __restrict__ size, float* __restrict__ mask, int* __restrict__ err) {
+    pdl_prologue();
     __shared__ EncBox s_box[kEncMaxBoxes];
     const int b = blockIdx.y;
     for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
@@ -108,6 +109,7 @@ encode_targets_kernel(const float* __restrict__ boxes, const int* __restrict__ l
 __global__ void __launch_bounds__(256)
 normalize_u8_kernel(const uint32_t* __restrict__ img, float* __restrict__ out, long long quads_per_img, float m0, float m1,
                     float m2, float s0, float s1, float s2) {
+    pdl_prologue();
     const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= quads_per_img) return;
     const int b = blockIdx.y;
@@ -143,8 +145,7 @@ extern "C" int hd_encode_targets(const float* boxes, const int* labels, int B, i
     HD_REQUIRE(scale_factor >= 1, "encode_targets: scale_factor=%d", scale_factor);
     HD_REQUIRE(heat && offset && size && mask && (nmax == 0 || (boxes && labels)), "encode_targets: null pointer");
     dim3 grid((h * w + 255) / 256, B);
-    encode_targets_kernel<<<grid, 256, 0, stream>>>(boxes, labels, nmax, h, w, num_cls, scale_factor, normalized, heat,
-                                                    offset, size, mask, err_count);
+    HD_CHECK_CUDA(::hd::launch_k(encode_targets_kernel, grid, 256, 0, stream, boxes, labels, nmax, h, w, num_cls, scale_factor, normalized, heat, offset, size, mask, err_count));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -160,8 +161,7 @@ extern "C" int hd_normalize_u8(const void* img_nhwc_u8, float* out_nchw, int B, 
                "normalize_u8: pointers must be 4 / 16 byte aligned");
     const long long quads = static_cast<long long>(H) * W / 4;
     dim3 grid(static_cast<unsigned>((quads + 255) / 256), B);
-    normalize_u8_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(img_nhwc_u8), out_nchw, quads,
-                                                  mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    HD_CHECK_CUDA(::hd::launch_k(normalize_u8_kernel, grid, 256, 0, stream, reinterpret_cast<const uint32_t*>(img_nhwc_u8), out_nchw, quads, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -66,6 +66,19 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+static int g_pdl = -1;
+static thread_local int t_pdl_scope = -1;     // PdlScope override of the calling thread (-1: none)
+int pdl_scope_set(int v) { int old = t_pdl_scope; t_pdl_scope = v; return old; }
+bool pdl_enabled() {
+    if (t_pdl_scope >= 0 && g_pdl != 0) return t_pdl_scope != 0;
+    if (g_pdl < 0) {
+        const char* e = getenv("HD_NO_PDL");
+        g_pdl = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -87,3 +100,5 @@ extern "C" int hd_version(void) { return 1; }
 namespace hd { long long launches(); }
 // Number of kernels this library has launched in this process (bench.py reports it as gpu_launches).
 extern "C" long long hd_launch_count(void) { return hd::launches(); }
+namespace hd { void set_pdl(int on); }
+extern "C" void hd_set_pdl(int on) { hd::set_pdl(on); }

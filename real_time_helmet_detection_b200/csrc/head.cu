@@ -20,6 +20,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, long long bs, int HW, int cou
                 const __nv_bfloat16* __restrict__ extra, int extra_cs, const __nv_bfloat16* __restrict__ feat,
                 const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw,
                 float* __restrict__ dbias, long long npix) {
+    pdl_prologue();
     __shared__ float s_w[MAXC][128];
     __shared__ float s_g[MAXC][kHeadTile];
     __shared__ float s_red[16][MAXC * 8 + 1];
@@ -136,20 +137,11 @@ extern "C" int hd_head_backward(const float* dlogits, long long bs, const void* 
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     if (cout <= 6)
-        head_bwd_kernel<6><<<static_cast<unsigned>(g), 256, 0, stream>>>(
-            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
-            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
-            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<6>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     else if (cout <= 8)
-        head_bwd_kernel<8><<<static_cast<unsigned>(g), 256, 0, stream>>>(
-            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
-            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
-            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<8>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     else
-        head_bwd_kernel<16><<<static_cast<unsigned>(g), 256, 0, stream>>>(
-            dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
-            reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp),
-            reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix);
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<16>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -57,6 +57,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 }
 
 __global__ void loss_fwd_kernel(const LossArgs a, float* __restrict__ sums) {
+    pdl_prologue();
     __shared__ float scratch[32];
     float s_mask = 0.f, s_pos = 0.f, s_neg = 0.f, s_off = 0.f, s_size = 0.f;
     const long long total = static_cast<long long>(a.B) * a.HW;
@@ -95,6 +96,7 @@ __global__ void loss_fwd_kernel(const LossArgs a, float* __restrict__ sums) {
 // out: [hm, offset, size, total, inv_norm]
 __global__ void loss_finalize_kernel(const float* __restrict__ sums, float* __restrict__ out, float B, float w_hm,
                                      float w_off, float w_size) {
+    pdl_prologue();
     const float np = fminf(fmaxf(sums[0], 1.f), 1e30f);
     const float inv = 1.f / np;
     const float hm = -((sums[1] / B) + (sums[2] / B)) * inv;
@@ -117,6 +119,7 @@ struct LossBwdArgs {
 };
 
 __global__ void loss_bwd_kernel(const LossArgs a, const LossBwdArgs g) {
+    pdl_prologue();
     const float up = g.grad_out ? *g.grad_out : 1.f;
     const float inv = g.fwd_out[4] * up;
     const long long total = static_cast<long long>(a.B) * a.HW;
@@ -190,9 +193,9 @@ extern "C" int hd_loss_forward(const float* hm, long long hm_bs, const float* of
                        from_logits, sigmoid_reg);
     if (rc) return rc;
     HD_CHECK_CUDA(cudaMemsetAsync(sums, 0, 5 * sizeof(float), stream));
-    loss_fwd_kernel<<<loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream>>>(a, sums);
+    HD_CHECK_CUDA(::hd::launch_k(loss_fwd_kernel, loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream, a, sums));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
-    loss_finalize_kernel<<<1, 1, 0, stream>>>(sums, out, static_cast<float>(B), w_hm, w_off, w_size);
+    HD_CHECK_CUDA(::hd::launch_k(loss_finalize_kernel, 1, 1, 0, stream, sums, out, static_cast<float>(B), w_hm, w_off, w_size));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -212,7 +215,7 @@ extern "C" int hd_loss_backward(const float* hm, long long hm_bs, const float* o
     g.d_hm = d_hm; g.d_hm_bs = d_hm_bs; g.d_off = d_off; g.d_off_bs = d_off_bs; g.d_size = d_size;
     g.d_size_bs = d_size_bs; g.fwd_out = fwd_out; g.grad_out = grad_out;
     g.w_hm = w_hm; g.w_off = w_off; g.w_size = w_size;
-    loss_bwd_kernel<<<loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream>>>(a, g);
+    HD_CHECK_CUDA(::hd::launch_k(loss_bwd_kernel, loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream, a, g));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

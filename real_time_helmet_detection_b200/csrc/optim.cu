@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
                                                          const float* __restrict__ step_dev,
                                                          const float* __restrict__ grad_scale,
                                                          const float* __restrict__ found_inf) {
+    pdl_prologue();
     if (found_inf && *found_inf != 0.f) return;          // GradScaler: skip the whole step on inf / nan gradients
     const long long chunk = blockIdx.x;
     if (chunk >= nchunks) return;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
 }
 
 __global__ void adam_advance_step_kernel(float* step_dev, const float* found_inf) {
+    pdl_prologue();
     if (!(found_inf && *found_inf != 0.f)) *step_dev += 1.f;
 }
 
@@ -69,11 +71,9 @@ extern "C" int hd_adam_step(const void* jobs_host, int njobs, void* jobs_dev, lo
     HD_REQUIRE(nchunks < (1ll << 31), "adam_step: too many chunks");
     HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(AdamJob),
                                   cudaMemcpyHostToDevice, stream));
-    adam_multi_kernel<<<static_cast<unsigned>(nchunks), 256, 0, stream>>>(
-        reinterpret_cast<const AdamJob*>(jobs_dev), njobs, nchunks, lr, beta1, beta2, eps, step_dev, grad_scale,
-        found_inf);
+    HD_CHECK_CUDA(::hd::launch_k(adam_multi_kernel, static_cast<unsigned>(nchunks), 256, 0, stream,  reinterpret_cast<const AdamJob*>(jobs_dev), njobs, nchunks, lr, beta1, beta2, eps, step_dev, grad_scale, found_inf));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
-    adam_advance_step_kernel<<<1, 1, 0, stream>>>(step_dev, found_inf);
+    HD_CHECK_CUDA(::hd::launch_k(adam_advance_step_kernel, 1, 1, 0, stream, step_dev, found_inf));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -10,6 +10,7 @@ namespace hd {
 // mode 1 (dgrad)  : out[tap][r = ci][k = co] = w[co][ci][taps-1-tap]   (180-degree rotated taps, transposed)
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
                                    int taps, int rows_pad, int k_pad, int mode) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = taps * rows_pad * k_pad;
     if (idx >= total) return;
@@ -28,6 +29,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // x: [N, C, H, W] fp32 -> y: [N, H, W, c_pad] bf16 (channels >= C zero-filled)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int H,
                                     int W, int c_pad) {
+    pdl_prologue();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t total = static_cast<size_t>(N) * H * W * c_pad;
     if (idx >= total) return;
@@ -44,6 +46,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 // x: [N, H, W, c_stride] bf16 -> y: [N, C, H, W] fp32
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int H,
                                     int W, int c_stride) {
+    pdl_prologue();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const size_t total = static_cast<size_t>(N) * C * H * W;
     if (idx >= total) return;
@@ -64,6 +67,7 @@ struct PackJob {
 };
 
 __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
+    pdl_prologue();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     int lo = 0, hi = njobs - 1;          // last job with start <= idx
@@ -95,8 +99,7 @@ extern "C" int hd_pack_all_weights(const void* jobs, int njobs, long long total,
     HD_REQUIRE(njobs > 0 && total > 0, "pack_all_weights: empty job table");
     const long long blocks = (total + 255) / 256;
     HD_REQUIRE(blocks < (1ll << 31), "pack_all_weights: too many elements");
-    pack_all_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs), njobs,
-                                                                      total);
+    HD_CHECK_CUDA(::hd::launch_k(pack_all_kernel, static_cast<unsigned>(blocks), 256, 0, stream, reinterpret_cast<const PackJob*>(jobs), njobs, total));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -108,8 +111,7 @@ extern "C" int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int
     const int rows = mode == 0 ? cout : cin, kdim = mode == 0 ? cin : cout;
     HD_REQUIRE(rows_pad >= rows && k_pad >= kdim, "pack_conv_weight: padding smaller than the matrix");
     const int total = ksize * ksize * rows_pad * k_pad;
-    pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(out), cout,
-                                                                cin, ksize * ksize, rows_pad, k_pad, mode);
+    HD_CHECK_CUDA(::hd::launch_k(pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w_oihw, reinterpret_cast<__nv_bfloat16*>(out), cout, cin, ksize * ksize, rows_pad, k_pad, mode));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -120,8 +122,7 @@ extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, i
     HD_REQUIRE(c_pad >= C, "nchw_to_nhwc: c_pad < C");
     const size_t total = static_cast<size_t>(N) * H * W * c_pad;
     if (total == 0) return HD_OK;
-    nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), N,
-                                                                            C, H, W, c_pad);
+    HD_CHECK_CUDA(::hd::launch_k(nchw_to_nhwc_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, c_pad));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -132,8 +133,7 @@ extern "C" int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, i
     HD_REQUIRE(c_stride >= C, "nhwc_to_nchw: c_stride < C");
     const size_t total = static_cast<size_t>(N) * C * H * W;
     if (total == 0) return HD_OK;
-    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                            y, N, C, H, W, c_stride);
+    HD_CHECK_CUDA(::hd::launch_k(nhwc_to_nchw_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), y, N, C, H, W, c_stride));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

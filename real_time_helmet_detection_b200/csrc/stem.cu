@@ -19,6 +19,7 @@ constexpr int kPH = 2 * kTOH + 5, kPW = 2 * kTOW + 5;
 
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                            int N, int H, int W) {
+    pdl_prologue();
     __shared__ float patch[3][kPH][kPW + 1];
     __shared__ short koff[kStemKPad];      // k -> offset inside the patch of the pixel at (0,0); -1 for the zero padding
     const int Ho = H >> 1, Wo = W >> 1;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 
 // w: [64][3][7][7] fp32 -> out: [1][64][192] bf16 in the im2col K order
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout) {
+    pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cout * kStemKPad) return;
     const int k = idx % kStemKPad, co = idx / kStemKPad;
@@ -86,8 +88,7 @@ extern "C" int hd_stem_im2col(const float* x, void* patches, int N, int H, int W
     const int Ho = H / 2, Wo = W / 2;
     const long long tiles = static_cast<long long>(N) * ((Ho + kTOH - 1) / kTOH) * ((Wo + kTOW - 1) / kTOW);
     HD_REQUIRE(tiles < (1ll << 31), "stem_im2col: too many tiles");
-    stem_im2col_kernel<<<static_cast<unsigned>(tiles), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches),
-                                                                        N, H, W);
+    HD_CHECK_CUDA(::hd::launch_k(stem_im2col_kernel, static_cast<unsigned>(tiles), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(patches), N, H, W));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -96,7 +97,7 @@ extern "C" int hd_stem_pack_weight(const float* w, void* out, int cout, cudaStre
     using namespace hd;
     HD_REQUIRE(cout > 0 && cout <= 64, "stem_pack_weight: cout=%d", cout);
     const int total = cout * kStemKPad;
-    stem_pack_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), cout);
+    HD_CHECK_CUDA(::hd::launch_k(stem_pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w, reinterpret_cast<__nv_bfloat16*>(out), cout));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -78,7 +78,8 @@ int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void* out, const
                            int block_n, int ksize, int out_cs, hd_stream_t stream);
 /* Eval-mode BatchNorm folded to scale / shift for a whole table of layers in one launch. jobs_host: njobs records
  * {const float* gamma, beta, running_mean, running_var; float* out; int channels; float eps} (out[0..C) = scale =
- * gamma * rsqrt(var + eps), out[C..2C) = shift = beta - mean * scale); jobs_dev: device scratch of the same size. */
+ * gamma * rsqrt(var + eps), out[C..2C) = shift = beta - mean * scale); jobs_dev: device scratch of the same size
+ * (jobs_host may be NULL when the table is already in jobs_dev). */
 int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, hd_stream_t stream);
 
 /* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the

@@ -694,10 +694,12 @@ __global__ void bn_fold_all_kernel(const BnFoldJob* __restrict__ jobs) {
 
 extern "C" int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, cudaStream_t stream) {
     using namespace hd;
-    HD_REQUIRE(njobs > 0 && jobs_host && jobs_dev, "bn_fold_all: empty job table");
-    // small pageable -> device copy, stream-ordered (the runtime stages the source before returning)
-    HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(BnFoldJob),
-                                  cudaMemcpyHostToDevice, stream));
+    HD_REQUIRE(njobs > 0 && jobs_dev, "bn_fold_all: empty job table");
+    // small pageable -> device copy, stream-ordered (the runtime stages the source before returning); jobs_host == NULL:
+    // the caller has already put the table into jobs_dev
+    if (jobs_host)
+        HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(BnFoldJob),
+                                      cudaMemcpyHostToDevice, stream));
     HD_CHECK_CUDA(::hd::launch_k(bn_fold_all_kernel, njobs, 128, 0, stream, reinterpret_cast<const BnFoldJob*>(jobs_dev)));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;

@@ -111,7 +111,11 @@ struct hd_net {
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> events;
     size_t ev_next = 0;
+    // pinned staging slots for the job tables of forwards recorded into a CUDA graph (see upload_table)
+    uint8_t* pinned = nullptr;
+    int pinned_next = 0;
     ~hd_net() {
+        if (pinned) cudaFreeHost(pinned);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (side) cudaStreamDestroy(side);
         if (alt_stream) cudaStreamDestroy(alt_stream);
@@ -234,6 +238,30 @@ extern "C" int hd_pack_all_weights(const void* jobs, int njobs, long long total,
 
 // One launch repacks every conv weight (fp32 OIHW master -> bf16 UMMA operands). The job table lives in the
 // persistent arena and is uploaded with every forward (parameters may have moved).
+// Host job table -> device, stream-ordered. Eager execution: a pageable source (the runtime stages it before
+// returning, so the host vector may die). While the stream is being CAPTURED into a CUDA graph a pageable copy is
+// illegal and the source must outlive the graph: the table goes into a pinned slot that stays untouched for the
+// lifetime of the network (the memcpy node re-reads it on every replay; the pointers in it are the captured ones).
+constexpr int kPinnedSlots = 32;
+constexpr size_t kPinnedSlotBytes = 8192;
+static void upload_table(hd_net* n, void* dst, const void* src, size_t bytes) {
+    if (n->dry || n->rc != 0) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(n->stream, &st) != cudaSuccess) { n->rc = fail(HD_ERR_CUDA, "net: cudaStreamIsCapturing failed"); return; }
+    if (st == cudaStreamCaptureStatusActive) {
+        if (!n->pinned || n->pinned_next >= kPinnedSlots || bytes > kPinnedSlotBytes) {
+            n->rc = fail(HD_ERR_UNSUPPORTED, "net: cannot record this forward into a CUDA graph (%s)",
+                         !n->pinned ? "run one eager forward first" : "more than 16 graphs captured on one network");
+            return;
+        }
+        uint8_t* slot = n->pinned + static_cast<size_t>(n->pinned_next++) * kPinnedSlotBytes;
+        memcpy(slot, src, bytes);
+        src = slot;
+    }
+    if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, n->stream) != cudaSuccess)
+        n->rc = fail(HD_ERR_CUDA, "net_forward: upload of a job table failed");
+}
+
 static void pack_weights(hd_net* n, bool need_dgrad) {
     std::vector<PackJobHost> jobs;
     long long total = 0;
@@ -255,11 +283,7 @@ static void pack_weights(hd_net* n, bool need_dgrad) {
             j.start = total; total += static_cast<long long>(j.taps) * j.rows_pad * j.k_pad; jobs.push_back(j);
         }
     }
-    const size_t bytes = jobs.size() * sizeof(PackJobHost);
-    // 3.6 KB pageable -> device copy per forward: stream-ordered, and the host vector may die when the call returns
-    // (the runtime stages pageable sources before returning)
-    if (n->rc == 0 && cudaMemcpyAsync(n->pack_jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice, n->stream) != cudaSuccess)
-        n->rc = fail(HD_ERR_CUDA, "net_forward: upload of the weight-pack table failed");
+    upload_table(n, n->pack_jobs_dev, jobs.data(), jobs.size() * sizeof(PackJobHost));
     RUN(hd_pack_all_weights(n->pack_jobs_dev, static_cast<int>(jobs.size()), total, n->stream));
 }
 
@@ -278,7 +302,9 @@ static void fold_bn(hd_net* n) {
         const hd_unit_ptrs& p = UP(n, static_cast<int>(i));
         jobs.push_back(BnFoldJobHost{p.gamma, p.beta, p.running_mean, p.running_var, u.bnp, u.cout, 1e-5f});
     }
-    if (!jobs.empty()) RUN(hd_bn_fold_all(jobs.data(), static_cast<int>(jobs.size()), n->fold_jobs_dev, n->stream));
+    if (jobs.empty()) return;
+    upload_table(n, n->fold_jobs_dev, jobs.data(), jobs.size() * sizeof(BnFoldJobHost));
+    RUN(hd_bn_fold_all(nullptr, static_cast<int>(jobs.size()), n->fold_jobs_dev, n->stream));
 }
 
 static cudaEvent_t next_event(hd_net* n) {
@@ -704,6 +730,16 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
     size_t head = 0;
     PdlScope pdl(training == 0);    // see hd_common.h: PDL pays off for the latency-bound eval pass only
     n->dry = false; n->rc = 0; n->up = units; n->stream = stream;
+    {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &st);
+        if (st == cudaStreamCaptureStatusNone) {      // resources are created by eager calls only
+            if (!n->pinned && cudaHostAlloc(reinterpret_cast<void**>(&n->pinned), kPinnedSlots * kPinnedSlotBytes,
+                                            cudaHostAllocDefault) != cudaSuccess)
+                return fail(HD_ERR_CUDA, "net_forward: cannot allocate the pinned job-table slots");
+            if (n->events.empty()) next_event(n);
+        }
+    }
     if (!n->alt_stream && cudaStreamCreateWithFlags(&n->alt_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(HD_ERR_CUDA, "net_forward: cannot create the second lane's stream");
     static const bool single_lane = getenv("HD_SINGLE_LANE") != nullptr;   // debug knob: everything on one stream

@@ -155,3 +155,26 @@ def test_amp_gradscaler_and_adam_step(cuda_device):
     assert network_out.dtype == torch.float32 and all(np.isfinite(losses))
     assert losses[-1] < losses[0]                          # three Adam steps on one batch reduce the loss
     assert len(crit.log["total"]) == 3
+
+
+def test_prediction_cuda_graph_matches_eager(cuda_device):
+    """Prediction(cuda_graph=True): eval forward (two streams, PDL launches, pinned job tables) + decode recorded into
+    a CUDA graph and replayed on new inputs == the eager path, bit for bit (the eval pass has no atomics)."""
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.evaluate import Prediction
+    torch.manual_seed(11)
+    net = StackedHourglass(2, 128, 6).to(cuda_device).eval()
+    eager = Prediction(net, 50, 4, 0.3, "nms", 0.3)
+    graphed = Prediction(net, 50, 4, 0.3, "nms", 0.3, cuda_graph=True)
+    for i, B in enumerate((2, 2, 1, 2)):          # second shape -> second graph; first shape replayed again
+        x = torch.randn(B, 3, 128, 128, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(i))
+        be, ce, se = eager(x)
+        bg, cg, sg = graphed(x)
+        assert len(bg) == B
+        for b in range(B):
+            assert se[b].numel() > 0
+            assert torch.equal(be[b], bg[b]) and torch.equal(ce[b], cg[b]) and torch.equal(se[b], sg[b])
+    assert len(graphed._graphs) == 2
+    net.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        Prediction(net, 50, 4, 0.3, "nms", 0.3, cuda_graph=True)(torch.randn(1, 3, 64, 64, device=cuda_device))

@@ -9,8 +9,8 @@ from real_time_helmet_detection_b200.evaluate import Prediction
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = StackedHourglass(1, 128, 6).to(dev).eval()
-pred = Prediction(net, 100, 4, 0.2, "nms", 0.2)
-for B in (1, 8):
+for B, graph in ((1, False), (1, True), (8, False), (8, True)):
+    pred = Prediction(net, 100, 4, 0.2, "nms", 0.2, cuda_graph=graph)
     x = torch.randn(B, 3, 512, 512, device=dev)
     for _ in range(5):
         pred(x)
@@ -26,4 +26,4 @@ for B in (1, 8):
         with torch.no_grad():
             net(x)
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B}: predict wall {statistics.median(wall)*1e3:.3f} ms/batch ({B/statistics.median(wall):.0f} img/s) | forward-only device {e0.elapsed_time(e1)/50:.3f} ms")
+    print(f"B={B} cuda_graph={graph}: predict wall {statistics.median(wall)*1e3:.3f} ms/batch ({B/statistics.median(wall):.0f} img/s) | forward-only device {e0.elapsed_time(e1)/50:.3f} ms")

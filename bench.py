@@ -357,7 +357,7 @@ def run_ours(args):
         time.sleep(0.3)
     ms, launches, t0, t1 = timed(step_device, args.steps)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    for _ in range(2):
+    for _ in range(max(args.warmup, 5)):    # the prefetch stream's allocator blocks need a few steps to settle
         step_e2e()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
     crit.log = {k: [] for k in ("hm", "offset", "size", "total")}

@@ -85,5 +85,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+RUNNER_SRC = os.path.join(os.path.dirname(PKG_DIR), "runner", "hd_infer.cpp")
+RUNNER_BIN = os.path.join(os.path.dirname(PKG_DIR), "runner", "hd_infer")
+
+
+def build_runner(force: bool = False) -> str:
+    """Native inference runner (runner/hd_infer.cpp): plain C++ over the C ABI, linked against the in-tree .so."""
+    lib = build()
+    if (not force and os.path.exists(RUNNER_BIN) and os.path.getmtime(RUNNER_BIN) > os.path.getmtime(RUNNER_SRC)
+            and os.path.getmtime(RUNNER_BIN) > os.path.getmtime(lib)):
+        return RUNNER_BIN
+    cmd = [_nvcc(), "-O2", "-std=c++17", RUNNER_SRC, "-o", RUNNER_BIN + ".tmp",
+           "-I", os.path.join(os.path.dirname(PKG_DIR), "include"), "-L", PKG_DIR, "-lhd_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../real_time_helmet_detection_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"runner build failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(RUNNER_BIN + ".tmp", RUNNER_BIN)
+    return RUNNER_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_runner(force="--force" in sys.argv))

@@ -140,7 +140,10 @@ int hd_bn_bwd_reduce(const void* dout, const void* out, const float* act_scale, 
                      const void* y, const float* mean, const float* rstd,
                      const void* ys, const float* mean_s, const float* rstd_s, float* sums, long long npix, int C,
                      hd_stream_t stream);
-/* Same reduction with the finalize fused in: the last block to add its partial sums also computes coef (and coef_s),
+/* out == NULL: the ReLU mask is rebuilt instead of read - from y*act_scale+act_shift (conv+BN+ReLU unit), or, when ys
+ * is given, from y*act_scale+act_shift + ys*act_scale_s+act_shift_s (two-branch residual tail, hourglass.py:125-127);
+ * act_scale_s / act_shift_s are only needed in that last case (hd_bn_bwd_reduce_fin and hd_bn_bwd_apply).
+ * Same reduction with the finalize fused in: the last block to add its partial sums also computes coef (and coef_s),
  * dgamma / dbeta (and the skip branch's) exactly like hd_bn_bwd_finalize, then re-zeroes `sums`.
  * `counter`: zero-initialised device word (left at zero). */
 typedef struct hd_bn_bwd_fuse {
@@ -150,14 +153,15 @@ typedef struct hd_bn_bwd_fuse {
     unsigned int* counter;
 } hd_bn_bwd_fuse;
 int hd_bn_bwd_reduce_fin(const void* dout, const void* out, const float* act_scale, const float* act_shift,
-                         const void* y, const void* ys, float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin,
-                         hd_stream_t stream);
+                         const float* act_scale_s, const float* act_shift_s, const void* y, const void* ys,
+                         float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin, hd_stream_t stream);
 int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
                        const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
                        hd_stream_t stream);
 int hd_bn_bwd_apply(const void* dout, const void* out, const float* act_scale, const float* act_shift,
-                    const void* y, const float* coef, void* dy, const void* ys,
-                    const float* coef_s, void* dys, void* gout, long long npix, int C, hd_stream_t stream);
+                    const float* act_scale_s, const float* act_shift_s, const void* y, const float* coef, void* dy,
+                    const void* ys, const float* coef_s, void* dys, void* gout, long long npix, int C,
+                    hd_stream_t stream);
 int hd_maxpool2_bwd(const void* x, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
                     int W, int C, hd_stream_t stream);
 int hd_sum2x2(const void* dout, void* dlow, int N, int H, int W, int C, hd_stream_t stream);

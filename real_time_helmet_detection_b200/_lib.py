@@ -46,8 +46,9 @@ _SIGNATURES = {
     "hd_maxpool2": (I, [P, P, I, I, I, I, P]),
     "hd_upsample2_add": (I, [P, P, P, I, I, I, I, P]),
     "hd_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),
+    "hd_bn_bwd_reduce_fin": (I, [P, P, P, P, P, P, P, P, P, LL, I, P, P]),
     "hd_bn_bwd_finalize": (I, [P, P, F, P, P, P, P, P, P, I, I, P]),
-    "hd_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),
+    "hd_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),
     "hd_maxpool2_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "hd_sum2x2": (I, [P, P, I, I, I, I, P]),
     "hd_add": (I, [P, P, P, P, LL, P]),

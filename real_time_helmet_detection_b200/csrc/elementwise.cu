@@ -201,9 +201,10 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const
 // the ReLU mask of a plain conv+BN+ReLU is recomputed as y*scale+shift > 0, which saves reading the activated tensor),
 // so the kernel stays at ~50 registers and runs at HBM speed.
 template <bool SECOND, bool REMASK>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, SECOND ? 2 : 4)      // the two-BN variants need > 64 registers (they spilled at 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                     const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
                      float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin) {
     pdl_prologue();
@@ -213,11 +214,15 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     const int row = threadIdx.x / cvec;             // pixel lane inside the block
     const int rows = blockDim.x / cvec;
     const int c0 = lane_c << 3;
-    float asc[8], ash[8];
+    // REMASK && SECOND: two-branch residual tail relu(bn(y) + bn_s(ys)) - the mask is rebuilt from both conv outputs,
+    // which this kernel reads anyway, exactly as bn_add_relu_kernel<true> computed it
+    float asc[8], ash[8], asc2[8], ash2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         asc[j] = REMASK ? act_scale[c0 + j] : 0.f;
         ash[j] = REMASK ? act_shift[c0 + j] : 0.f;
+        asc2[j] = (REMASK && SECOND) ? act_scale_s[c0 + j] : 0.f;
+        ash2[j] = (REMASK && SECOND) ? act_shift_s[c0 + j] : 0.f;
     }
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
     float a0[8], a1[8], a2[8];
@@ -233,7 +238,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         if (SECOND) y2 = load8(ys + off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float pre = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) : o.v[j];
+            float pre = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) : o.v[j];
+            if (REMASK && SECOND) pre += fmaf(y2.v[j], asc2[j], ash2[j]);
             const float gj = pre > 0.f ? g.v[j] : 0.f;
             a0[j] += gj;
             a1[j] = fmaf(gj, yy.v[j], a1[j]);
@@ -326,18 +332,21 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
 
 // g = dout * (out > 0);  dy = a*g + b*y + c ; optionally dys = as*g + bs*ys + cs ; optionally gout = g
 template <bool SECOND, bool WRITE_G>
-__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, SECOND ? 2 : 4) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                                    const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
                                     const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
                                     __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
     pdl_prologue();
-    __shared__ __align__(16) float p[8][256];
+    __shared__ __align__(16) float p[10][256];
     const bool remask = out == nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         p[6][i] = remask ? act_scale[i] : 0.f;
         p[7][i] = remask ? act_shift[i] : 0.f;
+        p[8][i] = (remask && SECOND) ? act_scale_s[i] : 0.f;
+        p[9][i] = (remask && SECOND) ? act_shift_s[i] : 0.f;
         p[0][i] = coef[i];
         p[1][i] = coef[C + i];
         p[2][i] = coef[2 * C + i];
@@ -358,16 +367,22 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const __nv_bfloat1
         F8 g = load8(dout + i * 8);
         F8 yy = load8(y + i * 8);
         F8 o, r, r2, y2;
+        if (SECOND) y2 = load8(ys + i * 8);
         if (remask) {
             float asc[8], ash[8];
             lds8(p[6], c0, asc);
             lds8(p[7], c0, ash);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], asc[j], ash[j]);
+            if (SECOND) {       // two-branch residual tail: relu(bn(y) + bn_s(ys)), as bn_add_relu_kernel<true>
+                lds8(p[8], c0, asc);
+                lds8(p[9], c0, ash);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] += fmaf(y2.v[j], asc[j], ash[j]);
+            }
         } else {
             o = load8(out + i * 8);
         }
-        if (SECOND) y2 = load8(ys + i * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
@@ -571,19 +586,17 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y, cvp ys,
-                                    float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin, cudaStream_t stream);
-
 extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
                                 const float* mean, const float* rstd, cvp ys, const float* mean_s,
                                 const float* rstd_s, float* sums, long long npix, int C, cudaStream_t stream) {
     (void)mean; (void)rstd; (void)mean_s; (void)rstd_s;   // the sums are raw moments; hd_bn_bwd_finalize applies mean / rstd
-    return hd_bn_bwd_reduce_fin(dout, out, act_scale, act_shift, y, ys, sums, npix, C, nullptr, stream);
+    HD_REQUIRE(out != nullptr || ys == nullptr, "bn_bwd_reduce: a two-branch tail without `out` needs hd_bn_bwd_reduce_fin");
+    return hd_bn_bwd_reduce_fin(dout, out, act_scale, act_shift, nullptr, nullptr, y, ys, sums, npix, C, nullptr, stream);
 }
 
-extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y, cvp ys,
-                                    float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin_in,
-                                    cudaStream_t stream) {
+extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift,
+                                    const float* act_scale_s, const float* act_shift_s, cvp y, cvp ys, float* sums,
+                                    long long npix, int C, const hd_bn_bwd_fuse* fin_in, cudaStream_t stream) {
     hd_bn_bwd_fuse fin{};
     if (fin_in) fin = *fin_in;
     HD_REQUIRE(fin.coef == nullptr || (fin.counter && fin.gamma && fin.mean && fin.rstd && fin.count > 0.f),
@@ -592,19 +605,21 @@ extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, c
                "bn_bwd_reduce: fused finalize of the skip branch needs its gamma / mean / rstd / coef");
     HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
     HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_reduce: need `out` or the activation scale/shift");
+    HD_REQUIRE(out != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
+               "bn_bwd_reduce: rebuilding the mask of a two-branch tail needs the skip branch's scale/shift too");
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
     if (ys && out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, BF(y), BF(ys), sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin));
     else if (out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), nullptr, sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, BF(y), nullptr, sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -618,21 +633,25 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, const float* act_scale, const float* act_shift, cvp y,
-                               const float* coef, void* dy, cvp ys, const float* coef_s,
-                               void* dys, void* gout, long long npix, int C, cudaStream_t stream) {
+extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, const float* act_scale, const float* act_shift,
+                               const float* act_scale_s, const float* act_shift_s, cvp y, const float* coef, void* dy,
+                               cvp ys, const float* coef_s, void* dys, void* gout, long long npix, int C,
+                               cudaStream_t stream) {
     HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_bwd_apply: C=%d", C);
+    HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_apply: need `out` or the activation scale/shift");
+    HD_REQUIRE(out != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
+               "bn_bwd_apply: rebuilding the mask of a two-branch tail needs the skip branch's scale/shift too");
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
     if (ys && gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C));
     else if (gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

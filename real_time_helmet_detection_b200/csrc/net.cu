@@ -111,6 +111,10 @@ struct hd_net {
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> events;
     size_t ev_next = 0;
+    // HD_PHASE_TIMING=1: timing events on the caller's stream at the phase boundaries of forward / backward; the table
+    // is printed to stderr at the end of every backward pass (profiling aid, costs a device sync)
+    struct Phase { const char* name; cudaEvent_t ev; };
+    std::vector<Phase> phases;
     // pinned staging slots for the job tables of forwards recorded into a CUDA graph (see upload_table)
     uint8_t* pinned = nullptr;
     int pinned_next = 0;
@@ -121,6 +125,30 @@ struct hd_net {
         if (alt_stream) cudaStreamDestroy(alt_stream);
     }
 };
+
+static void phase_mark(hd_net* n, const char* name) {
+    static const bool on = getenv("HD_PHASE_TIMING") != nullptr;
+    if (!on || n->dry || n->rc != 0) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, n->stream);
+    n->phases.push_back({name, e});
+}
+static void phase_report(hd_net* n) {
+    if (n->phases.size() < 2) return;
+    cudaEventSynchronize(n->phases.back().ev);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, n->phases.front().ev, n->phases.back().ev);
+    fprintf(stderr, "[hd_net phases] total %.3f ms:", total);
+    for (size_t i = 1; i < n->phases.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, n->phases[i - 1].ev, n->phases[i].ev);
+        fprintf(stderr, "  %s %.3f", n->phases[i].name, ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto& ph : n->phases) cudaEventDestroy(ph.ev);
+    n->phases.clear();
+}
 
 static const hd_unit_ptrs kNullUnit{};
 static inline const hd_unit_ptrs& UP(const hd_net* n, int ui) { return n->up ? n->up[ui] : kNullUnit; }
@@ -440,6 +468,7 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
         pack_weights(n, training != 0);
         if (!training) fold_bn(n);
     }
+    phase_mark(n, "fwd:start");
     // ---- PreLayer (hourglass.py:159-173)
     Unit& u0 = n->units[0];
     n->patches = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 192)));
@@ -452,17 +481,21 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     } else {
         conv_unit(n, 0, n->patches, n->Z0, B, H2, W2, nullptr, 0, 1);
     }
+    phase_mark(n, "stem");
     bf16* r1 = residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training);
+    phase_mark(n, "pre1@256");
     n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
     RUN(hd_maxpool2(r1, n->R1pool, B, H2, W2, 128, n->stream));
     bf16* r3 = residual_fwd(n, n->r_pre3, n->R1pool, B, H4, W4, training);
     bf16* xcur = residual_fwd(n, n->r_pre4, r3, B, H4, W4, training);
+    phase_mark(n, "pool+pre3,4");
     // ---- stacks (hourglass.py:226-235)
     const long long npix4 = static_cast<long long>(B) * H4 * W4;
     for (int i = 0; i < n->S; ++i) {
         hd_net::StackSaved& s = n->stacks[i];
         s.x_in = xcur;
         s.hg_out = hourglass_fwd(n, s.hg_root, xcur, B, H4, W4, training);
+        phase_mark(n, "hourglass");
         Unit& un = n->units[s.u_neck];
         s.Yn = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
         s.F1 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
@@ -489,6 +522,7 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
             conv_unit(n, s.u_mp, s.pred64, xn, B, H4, W4, s.T, training);
             xcur = xn;
         }
+        phase_mark(n, "neck+head");
     }
 }
 
@@ -534,9 +568,14 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
         fin.gamma_s = ps.gamma; fin.mean_s = s->bnp + 2 * C; fin.rstd_s = s->bnp + 3 * C; fin.coef_s = coef_s;
         fin.dgamma_s = ps.dgamma; fin.dbeta_s = ps.dbeta;
     }
-    RUN(hd_bn_bwd_reduce_fin(dout, out, u.bnp, u.bnp + C, y, ys, sums, u.npix, C, &fin, n->stream));
-    RUN(hd_bn_bwd_apply(dout, out, u.bnp, u.bnp + C, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout, u.npix, C,
-                        n->stream));
+    // two-branch tail (skip conv + BN): the ReLU mask is rebuilt from the two conv outputs the kernels read anyway
+    // instead of reading the stored block output (saves a 537 MB read per kernel at 256x256)
+    const float* sc_s = s ? s->bnp : nullptr;
+    const float* sh_s = s ? s->bnp + C : nullptr;
+    const bf16* mask_src = s ? nullptr : out;
+    RUN(hd_bn_bwd_reduce_fin(dout, mask_src, u.bnp, u.bnp + C, sc_s, sh_s, y, ys, sums, u.npix, C, &fin, n->stream));
+    RUN(hd_bn_bwd_apply(dout, mask_src, u.bnp, u.bnp + C, sc_s, sh_s, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout,
+                        u.npix, C, n->stream));
 }
 
 static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
@@ -600,6 +639,7 @@ static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const b
 
 static void backward_impl(hd_net* n, const float* dlogits) {
     const int B = n->B, C = n->in_ch;
+    phase_mark(n, "(loss)bwd:start");
     const int H2 = n->H / 2, W2 = n->W / 2, H4 = n->H / 4, W4 = n->W / 4;
     const size_t full4 = act_bytes(B, H4, W4, C);
     const long long hw4 = static_cast<long long>(H4) * W4;
@@ -645,7 +685,9 @@ static void backward_impl(hd_net* n, const float* dlogits) {
         cudaEvent_t en = mark_ready(n);
         wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4, en);
         bf16* dXi = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+        phase_mark(n, "head+neck bwd");
         hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);
+        phase_mark(n, "hourglass bwd");
         dXn = dXi;
     }
     // PreLayer
@@ -653,10 +695,13 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     residual_bwd(n, n->r_pre4, dXn, dR3, B);
     bf16* dP = reinterpret_cast<bf16*>(n->bw.alloc(full4));
     residual_bwd(n, n->r_pre3, dR3, dP, B);
+    phase_mark(n, "pre4,3 bwd");
     bf16* dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
     RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    phase_mark(n, "pool bwd");
     bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     residual_bwd(n, n->r_pre1, dR1, dZ0, B);
+    phase_mark(n, "pre1@256 bwd");
     bf16* dY0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     bn_bwd_unit(n, 0, dZ0, nullptr, n->Y0, dY0, -1, nullptr, nullptr, nullptr);
     cudaEvent_t e0 = mark_ready(n);
@@ -665,8 +710,11 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     // join: everything the side stream produced (all weight gradients) is ordered before whatever follows on `stream`
     if (!n->dry && n->rc == 0) {
         cudaEvent_t done = next_event(n);
+        phase_mark(n, "stem bwd");
         if (!done || cudaEventRecord(done, n->side) != cudaSuccess || cudaStreamWaitEvent(n->stream, done, 0) != cudaSuccess)
             n->rc = fail(HD_ERR_CUDA, "net_backward: stream join failed");
+        phase_mark(n, "wgrad tail");
+        phase_report(n);
     }
 }
 

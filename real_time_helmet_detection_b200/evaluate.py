@@ -7,6 +7,11 @@ class-agnostic NMS) followed by a single device->host read of the per-image box 
 """
 from __future__ import annotations
 
+import os
+import pickle
+import time
+
+import numpy as np
 import torch
 
 from . import _lib
@@ -96,3 +101,59 @@ class Prediction(torch.nn.Module):
         with torch.no_grad():
             batch_output = self.network(x)       # b, n, num_cls+4, h, w
         return self.decode(batch_output)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Evaluation loop + on-disk formats of the reference (evaluate.py:40-112): `prediction_results.pickle`
+# ({image filename: float64 array (n, 6) = class, score, xmin, ymin, xmax, ymax in ORIGINAL image pixels}) and one
+# `txt/<name>.txt` per image ("%d %f %d %d %d %d" per detection) - the input of the mAP scorer (mAP/main.py).
+def resize_box_to_original_scale(boxes, original_size, transformed_size):
+    """(n,4) xyxy boxes in network-input pixels -> original image pixels (evaluate.py:101-112), vectorised."""
+    rw = original_size[0] / transformed_size[0]
+    rh = original_size[1] / transformed_size[1]
+    return np.asarray(boxes, dtype=np.float64).reshape(-1, 4) * np.array([rw, rh, rw, rh])
+
+
+def evaluate_step(dataloader, predictor, device, args):
+    """Same contract as the reference's `evaluate_step` (evaluate.py:59-99). One prediction call per batch; the
+    rescale to the original size and the (class, score, box) packing happen on the device, so every image costs one
+    small device->host copy instead of three."""
+    predictor.eval()
+    results = {}
+    t_data = t_fwd = 0.0
+    n_batches = 0
+    tic = time.time()
+    for image, _gt_heatmap, _gt_offset, _gt_size, _gt_mask, gt_dict in dataloader:
+        t_data += time.time() - tic
+        tic = time.time()
+        box_lst, cls_lst, score_lst = predictor(image.to(device))
+        t_fwd += time.time() - tic
+        n_batches += 1
+        for b in range(image.shape[0]):
+            ann = gt_dict[b]['annotation']
+            rw = int(ann['size']['width']) / args.imsize
+            rh = int(ann['size']['height']) / args.imsize
+            boxes, clss, scores = box_lst[b], cls_lst[b], score_lst[b]
+            if boxes.shape[0] != 0:
+                scale = torch.tensor([rw, rh, rw, rh], dtype=torch.float64, device=boxes.device)
+                packed = torch.cat([clss.to(torch.float64)[:, None], scores.to(torch.float64)[:, None],
+                                    boxes.to(torch.float64) * scale], dim=1)
+                results[ann['filename']] = packed.cpu().numpy()
+            else:
+                results[ann['filename']] = np.zeros((0, 6))
+        tic = time.time()
+    n_batches = max(n_batches, 1)
+    print('%s: Evaluation, Time(ms) [data: %6.2f, forward: %6.2f]'
+          % (time.ctime(), t_data / n_batches * 1000, t_fwd / n_batches * 1000))
+    return results
+
+
+def save_predictions(predictions, save_path):
+    """The two artefacts `evaluate.py:40-54` writes under --save-path."""
+    os.makedirs(os.path.join(save_path, 'txt'), exist_ok=True)
+    with open(os.path.join(save_path, 'prediction_results.pickle'), 'wb') as f:
+        pickle.dump(predictions, f, protocol=pickle.HIGHEST_PROTOCOL)
+    for filename, pred in predictions.items():
+        with open(os.path.join(save_path, 'txt', os.path.splitext(filename)[0] + '.txt'), 'w') as f:
+            for row in pred:
+                f.write('%d %f %d %d %d %d\n' % (row[0], row[1], row[2], row[3], row[4], row[5]))

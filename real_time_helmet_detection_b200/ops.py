@@ -186,10 +186,11 @@ def bn_bwd(dout, out, y, bnp, gamma, ys=None, bnp_s=None, gamma_s=None, want_g=F
     npix = y.numel() // C
     sums = torch.zeros((3, C), dtype=torch.float32, device=y.device)
     L = _lib.lib()
-    out_arg = None if remask else out     # remask: rebuild the ReLU mask from y*scale+shift instead of reading `out`
-    check(L.hd_bn_bwd_reduce(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]), ptr(y), ptr(bnp[2]), ptr(bnp[3]), ptr(ys),
-                             ptr(bnp_s[2]) if ys is not None else None, ptr(bnp_s[3]) if ys is not None else None,
-                             ptr(sums), npix, C, stream()), "bn_bwd_reduce")
+    # remask: rebuild the ReLU mask from y*scale+shift (+ ys*scale_s+shift_s for a two-branch tail) instead of reading `out`
+    out_arg = None if remask else out
+    check(L.hd_bn_bwd_reduce_fin(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]),
+                                 ptr(bnp_s[0]) if ys is not None else None, ptr(bnp_s[1]) if ys is not None else None,
+                                 ptr(y), ptr(ys), ptr(sums), npix, C, None, stream()), "bn_bwd_reduce")
     coef = torch.empty((3, C), dtype=torch.float32, device=y.device)
     dgamma = torch.empty(C, dtype=torch.float32, device=y.device)
     dbeta = torch.empty(C, dtype=torch.float32, device=y.device)
@@ -206,7 +207,9 @@ def bn_bwd(dout, out, y, bnp, gamma, ys=None, bnp_s=None, gamma_s=None, want_g=F
         dys = torch.empty_like(ys)
     dy = torch.empty_like(y)
     g = torch.empty_like(y) if want_g else None
-    check(L.hd_bn_bwd_apply(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]), ptr(y), ptr(coef), ptr(dy), ptr(ys),
+    check(L.hd_bn_bwd_apply(ptr(dout), ptr(out_arg), ptr(bnp[0]), ptr(bnp[1]),
+                            ptr(bnp_s[0]) if ys is not None else None, ptr(bnp_s[1]) if ys is not None else None,
+                            ptr(y), ptr(coef), ptr(dy), ptr(ys),
                             ptr(coef_s), ptr(dys), ptr(g),
                             npix, C, stream()), "bn_bwd_apply")
     return dy, dys, g, (dgamma, dbeta), (dgs, dbs)

@@ -111,3 +111,43 @@ def test_batched_prediction_vs_oracle(cuda_device):
         _pred(nms="soft-nms").decode(torch.from_numpy(heads).to(cuda_device))
     with pytest.raises(NotImplementedError):
         _pred(nms="bogus").decode(torch.from_numpy(heads).to(cuda_device))
+
+
+def test_evaluate_step_and_writers(cuda_device, tmp_path):
+    """evaluate_step + save_predictions reproduce the reference's eval artefacts (evaluate.py:40-99): dict of (n,6)
+    float64 arrays in original-image pixels, the pickle, and the "%d %f %d %d %d %d" txt lines."""
+    import pickle
+    import types
+    from real_time_helmet_detection_b200.evaluate import (Prediction, evaluate_step, save_predictions,
+                                                          resize_box_to_original_scale)
+    from real_time_helmet_detection_b200.synthetic import synthetic_head
+
+    class FakeNet(torch.nn.Module):           # a "network" that returns the config-5 blob head for every image
+        def forward(self, x):
+            return torch.from_numpy(synthetic_head(S=1)).to(x.device).repeat(x.shape[0], 1, 1, 1, 1)
+
+    pred = Prediction(FakeNet(), 100, 4, 0.2, "nms", 0.2)
+    sizes = [(640, 480), (500, 375), (512, 512)]
+    batches = [(torch.zeros(2, 3, 512, 512), None, None, None, None,
+                [{"annotation": {"filename": f"img{i}.jpg", "size": {"width": str(sizes[i][0]), "height": str(sizes[i][1])}}}
+                 for i in range(2)]),
+               (torch.zeros(1, 3, 512, 512), None, None, None, None,
+                [{"annotation": {"filename": "img2.jpg", "size": {"width": "512", "height": "512"}}}])]
+    args = types.SimpleNamespace(imsize=512)
+    res = evaluate_step(batches, pred, cuda_device, args)
+    boxes, clss, scores = pred(torch.zeros(1, 3, 512, 512, device=cuda_device))
+    assert sorted(res) == ["img0.jpg", "img1.jpg", "img2.jpg"]
+    for i in range(3):
+        r = res[f"img{i}.jpg"]
+        assert r.dtype == np.float64 and r.shape == (44, 6)
+        assert np.array_equal(r[:, 0], clss[0].cpu().numpy()) and np.allclose(r[:, 1], scores[0].cpu().numpy())
+        want = resize_box_to_original_scale(boxes[0].cpu().numpy(), sizes[i], (512, 512))
+        assert np.allclose(r[:, 2:], want, rtol=1e-6, atol=1e-4)
+    save_predictions(res, str(tmp_path))
+    back = pickle.load(open(tmp_path / "prediction_results.pickle", "rb"))
+    assert all(np.array_equal(back[k], res[k]) for k in res)
+    lines = open(tmp_path / "txt" / "img1.txt").read().splitlines()
+    assert len(lines) == 44
+    f0 = lines[0].split()
+    r = res["img1.jpg"][0]
+    assert int(f0[0]) == int(r[0]) and abs(float(f0[1]) - r[1]) < 1e-6 and [int(v) for v in f0[2:]] == [int(v) for v in r[2:]]

@@ -113,6 +113,14 @@ def test_bn_backward(cuda_device, skip_bn):
         dy2 = ops.bn_bwd(nhwc(dout, d), None, nhwc(yb, d), bnp, gamma.detach().to(d), remask=True)[0]
         close_bf16(nchw(dy2), yr.grad, extra=2e-3 * yr.grad.abs().max().item())
     if skip_bn:
+        # two-branch tail: identical results with the mask rebuilt from y and ys instead of read from `out`
+        r = ops.bn_bwd(nhwc(dout, d), None, nhwc(y.detach(), d), bnp, gamma.detach().to(d), ys=nhwc(ys.detach(), d),
+                       bnp_s=bnp_s, gamma_s=gamma_s.detach().to(d), want_g=True, remask=True)
+        # (elements whose pre-activation is within bf16 rounding of zero may flip: compare with tolerance)
+        close_bf16(nchw(r[0]), y.grad, extra=2e-3 * scale)
+        close_bf16(nchw(r[1]), ys.grad, extra=2e-3 * scale)
+        assert (nchw(r[2]) != nchw(gout)).float().mean() < 2e-3
+        assert torch.allclose(r[3][0].cpu(), gamma.grad, rtol=2e-3, atol=2e-3 * gamma.grad.abs().max().item())
         close_bf16(nchw(dys), ys.grad, extra=2e-3 * scale)
         assert torch.allclose(dgs.cpu(), gamma_s.grad, rtol=2e-3, atol=2e-3 * gamma_s.grad.abs().max().item())
     else:

@@ -164,6 +164,15 @@ int hd_bn_bwd_apply(const void* dout, const void* out, const float* act_scale, c
                     hd_stream_t stream);
 int hd_maxpool2_bwd(const void* x, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
                     int W, int C, hd_stream_t stream);
+/* `Residual` tail with a BN'd skip branch fused with the 2x2 max pool that follows it in the PreLayer
+ * (hourglass.py:165-166, 125-127): pooled [N][H/2][W/2][C] bf16 = maxpool2(relu(y2*s2+b2 + ys*ss+bs)) (values rounded
+ * to bf16 before the comparison, like the stored tensor would be) and idx [N][H/2][W/2][C] uint8 = window position
+ * (0..3, row-major) of the first maximum; the un-pooled block output is never written. hd_maxpool2_bwd_idx is the
+ * pool's backward from those indices (same semantics as hd_maxpool2_bwd, which recomputes them from x). */
+int hd_bn_add_relu_pool2(const void* y2, const float* s2, const float* b2, const void* ys, const float* ss,
+                         const float* bs, void* pooled, void* idx, int N, int H, int W, int C, hd_stream_t stream);
+int hd_maxpool2_bwd_idx(const void* idx, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
+                        int W, int C, hd_stream_t stream);
 int hd_sum2x2(const void* dout, void* dlow, int N, int H, int W, int C, hd_stream_t stream);
 int hd_add(const void* a, const void* b, const void* c, void* out, long long nelem, hd_stream_t stream);
 int hd_colsum(const void* x, float* out, long long npix, int C, int cs, hd_stream_t stream);

@@ -172,6 +172,95 @@ __global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     }
 }
 
+// Residual tail with a BN'd skip branch FUSED with the 2x2 max pool that follows it (PreLayer, hourglass.py:165-166):
+//   out = relu(y2*s2+b2 + ys*ss+bs) is never stored; pooled = max over the 2x2 window of the bf16-rounded out values,
+//   idx = position (0..3, row-major) of the FIRST maximum - what max_pool2d's backward routes the gradient to.
+// At 256x256, B=32 this saves writing (537 MB) and re-reading (537 MB) the block output; backward needs neither: the
+// ReLU mask is rebuilt from y2 / ys and the pool backward reads `idx` (67 MB).
+__global__ void __launch_bounds__(256, 2)
+bn_add_relu_pool_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ s2, const float* __restrict__ b2,
+                        const __nv_bfloat16* __restrict__ ys, const float* __restrict__ ss, const float* __restrict__ bs,
+                        __nv_bfloat16* __restrict__ pooled, uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+    pdl_prologue();
+    __shared__ __align__(16) float p[4][256];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        p[0][i] = s2[i]; p[1][i] = b2[i]; p[2][i] = ss[i]; p[3][i] = bs[i];
+    }
+    __syncthreads();
+    const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const int c0 = static_cast<int>(threadIdx.x % cvec) << 3;
+    float k0[8], k1[8], k2[8], k3[8];
+    lds8(p[0], c0, k0); lds8(p[1], c0, k1); lds8(p[2], c0, k2); lds8(p[3], c0, k3);
+    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        size_t pix = i / cvec;
+        const int ox = pix % Wo;
+        const int oy = (pix / Wo) % Ho;
+        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+        const size_t o00 = ((static_cast<size_t>(n) * H + 2 * oy) * W + 2 * ox) * C + c0;
+        const size_t offs[4] = {o00, o00 + C, o00 + static_cast<size_t>(W) * C, o00 + static_cast<size_t>(W) * C + C};
+        F8 best;
+        uint32_t bi[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const F8 a = load8(y2 + offs[k]), b = load8(ys + offs[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float o = __bfloat162float(__float2bfloat16_rn(
+                    fmaxf(fmaf(a.v[j], k0[j], k1[j]) + fmaf(b.v[j], k2[j], k3[j]), 0.f)));
+                if (k == 0 || o > best.v[j]) {
+                    best.v[j] = o;
+                    bi[j >> 2] = (bi[j >> 2] & ~(0xffu << (8 * (j & 3)))) | (static_cast<uint32_t>(k) << (8 * (j & 3)));
+                }
+            }
+        }
+        store8(pooled + i * 8, best);
+        *reinterpret_cast<uint2*>(idx + i * 8) = make_uint2(bi[0], bi[1]);
+    }
+}
+
+// Max-pool backward from stored argmax indices (see above): dx[window k] = (k == idx ? dpool : 0) [+ add1] [+ add2]
+__global__ void maxpool2_bwd_idx_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dpool,
+                                        const __nv_bfloat16* __restrict__ add1, const __nv_bfloat16* __restrict__ add2,
+                                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+    pdl_prologue();
+    const int cvec = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const size_t nvec = static_cast<size_t>(N) * Ho * Wo * cvec;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cv = i % cvec;
+        size_t pix = i / cvec;
+        const int ox = pix % Wo;
+        const int oy = (pix / Wo) % Ho;
+        const int n = pix / (static_cast<size_t>(Wo) * Ho);
+        const size_t o00 = ((static_cast<size_t>(n) * H + 2 * oy) * W + 2 * ox) * C + cv * 8;
+        const size_t offs[4] = {o00, o00 + C, o00 + static_cast<size_t>(W) * C, o00 + static_cast<size_t>(W) * C + C};
+        const F8 g = load8(dpool + i * 8);
+        const uint2 w = *reinterpret_cast<const uint2*>(idx + i * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            F8 r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t b = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xffu;
+                r.v[j] = b == static_cast<uint32_t>(k) ? g.v[j] : 0.f;
+            }
+            if (add1) {
+                const F8 a = load8(add1 + offs[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[j] += a.v[j];
+            }
+            if (add2) {
+                const F8 a = load8(add2 + offs[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r.v[j] += a.v[j];
+            }
+            store8(dx + offs[k], r);
+        }
+    }
+}
+
 // out[n,y,x,:] = up1[n,y,x,:] + low[n,y/2,x/2,:]   (nearest x2 upsample + add); H, W are the OUTPUT sizes
 __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low,
                                     __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
@@ -662,6 +751,30 @@ extern "C" int hd_maxpool2_bwd(cvp x, cvp dpool, cvp add1, cvp add2, void* dx, i
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
     HD_CHECK_CUDA(::hd::launch_k(maxpool2_bwd_kernel, ew_blocks(nvec), 256, 0, stream, BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_add_relu_pool2(cvp y2, const float* s2, const float* b2, cvp ys, const float* ss, const float* bs,
+                                    void* pooled, void* idx, int N, int H, int W, int C, cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && H % 2 == 0 && W % 2 == 0,
+               "bn_add_relu_pool2: shape (%d,%d,%d,%d)", N, H, W, C);
+    HD_REQUIRE(y2 && ys && s2 && b2 && ss && bs && pooled && idx, "bn_add_relu_pool2: null argument");
+    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_pool_kernel, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(ys), ss, bs,
+                                 BFW(pooled), reinterpret_cast<uint8_t*>(idx), N, H, W, C));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_maxpool2_bwd_idx(cvp idx, cvp dpool, cvp add1, cvp add2, void* dx, int N, int H, int W, int C,
+                                   cudaStream_t stream) {
+    HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd_idx: shape (%d,%d,%d,%d)", N, H, W, C);
+    const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (nvec == 0) return HD_OK;
+    HD_CHECK_CUDA(::hd::launch_k(maxpool2_bwd_idx_kernel, ew_blocks(nvec), 256, 0, stream,
+                                 reinterpret_cast<const uint8_t*>(idx), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -86,6 +86,7 @@ struct hd_net {
     const hd_unit_ptrs* up = nullptr;
     // saved top-level tensors
     bf16 *patches = nullptr, *Y0 = nullptr, *Z0 = nullptr, *R1pool = nullptr;
+    uint8_t* R1idx = nullptr;   // argmax of the PreLayer max pool (training: fused into the residual tail before it)
     int r_pre1 = -1, r_pre3 = -1, r_pre4 = -1;
     struct StackSaved {
         int hg_root, neck_res;
@@ -397,7 +398,10 @@ static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, i
                         block_n_for(u.cout), k, 0, u.cout, 0, 0, 1, n->stream));
 }
 
-static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int training) {
+// pooled / pool_idx (training, skip-BN residual only): the block output is consumed by a 2x2 max pool and nothing else, so
+// the tail kernel emits the pooled tensor + argmax directly and the un-pooled output is never materialised (r.Out = null).
+static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int training, bf16* pooled = nullptr,
+                          uint8_t* pool_idx = nullptr) {
     ResSaved& r = n->res[ri];
     r.X = X; r.H = H; r.W = W;
     const size_t bytes = act_bytes(B, H, W, r.cout);
@@ -406,7 +410,7 @@ static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int t
     r.Z1 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
     r.Y2 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
     r.Ys = r.us >= 0 ? reinterpret_cast<bf16*>(n->fw.alloc(bytes)) : nullptr;
-    r.Out = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    r.Out = pooled ? nullptr : reinterpret_cast<bf16*>(n->fw.alloc(bytes));
     Unit &u1 = n->units[r.u1], &u2 = n->units[r.u2];
     if (!training) {
         // relu(bn1(conv1)) -> Z1 ; [bn_s(conv_s) -> Ys] ; relu(bn2(conv2) + skip) -> Out : 2-3 launches
@@ -425,6 +429,11 @@ static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int t
     if (r.us >= 0) {
         Unit& us = n->units[r.us];
         conv_unit(n, r.us, X, r.Ys, B, H, W, nullptr, training);
+        if (pooled) {
+            RUN(hd_bn_add_relu_pool2(r.Y2, u2.bnp, u2.bnp + u2.cout, r.Ys, us.bnp, us.bnp + us.cout, pooled, pool_idx, B,
+                                     H, W, r.cout, n->stream));
+            return pooled;
+        }
         RUN(hd_bn_add_relu(r.Y2, u2.bnp, u2.bnp + u2.cout, r.Ys, us.bnp, us.bnp + us.cout, r.Out, npix, r.cout,
                            n->stream));
     } else {
@@ -482,10 +491,22 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
         conv_unit(n, 0, n->patches, n->Z0, B, H2, W2, nullptr, 0, 1);
     }
     phase_mark(n, "stem");
-    bf16* r1 = residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training);
+    static const bool no_pool_fuse = getenv("HD_NO_POOL_FUSE") != nullptr;
+    const bool fuse_pool = training && !no_pool_fuse && n->res[n->r_pre1].us >= 0;
+    bf16* r1 = nullptr;
+    if (fuse_pool) {
+        n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
+        n->R1idx = reinterpret_cast<uint8_t*>(n->fw.alloc(static_cast<size_t>(B) * H4 * W4 * 128));
+        residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training, n->R1pool, n->R1idx);
+    } else {
+        n->R1idx = nullptr;
+        r1 = residual_fwd(n, n->r_pre1, n->Z0, B, H2, W2, training);
+    }
     phase_mark(n, "pre1@256");
-    n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
-    RUN(hd_maxpool2(r1, n->R1pool, B, H2, W2, 128, n->stream));
+    if (!fuse_pool) {
+        n->R1pool = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, 128)));
+        RUN(hd_maxpool2(r1, n->R1pool, B, H2, W2, 128, n->stream));
+    }
     bf16* r3 = residual_fwd(n, n->r_pre3, n->R1pool, B, H4, W4, training);
     bf16* xcur = residual_fwd(n, n->r_pre4, r3, B, H4, W4, training);
     phase_mark(n, "pool+pre3,4");
@@ -697,7 +718,8 @@ static void backward_impl(hd_net* n, const float* dlogits) {
     residual_bwd(n, n->r_pre3, dR3, dP, B);
     phase_mark(n, "pre4,3 bwd");
     bf16* dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
-    RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    else RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
     phase_mark(n, "pool bwd");
     bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     residual_bwd(n, n->r_pre1, dR1, dZ0, B);

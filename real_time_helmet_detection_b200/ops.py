@@ -166,6 +166,24 @@ def bn_add_relu(y2, bnp2, skip, bnp_s=None):
     return out
 
 
+def bn_add_relu_pool2(y2, bnp2, ys, bnp_s):
+    """maxpool2(relu(bn(y2) + bn_s(ys))) without materialising the un-pooled tensor: (pooled bf16, argmax uint8)."""
+    n, h, w, c = y2.shape
+    pooled = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=y2.device)
+    idx = torch.empty((n, h // 2, w // 2, c), dtype=torch.uint8, device=y2.device)
+    check(_lib.lib().hd_bn_add_relu_pool2(ptr(y2), ptr(bnp2[0]), ptr(bnp2[1]), ptr(ys), ptr(bnp_s[0]), ptr(bnp_s[1]),
+                                          ptr(pooled), ptr(idx), n, h, w, c, stream()), "bn_add_relu_pool2")
+    return pooled, idx
+
+
+def maxpool2_bwd_idx(idx, dpool, add1=None, add2=None):
+    n, ho, wo, c = dpool.shape
+    dx = torch.empty((n, 2 * ho, 2 * wo, c), dtype=BF16, device=dpool.device)
+    check(_lib.lib().hd_maxpool2_bwd_idx(ptr(idx), ptr(dpool), ptr(add1), ptr(add2), ptr(dx), n, 2 * ho, 2 * wo, c,
+                                         stream()), "maxpool2_bwd_idx")
+    return dx
+
+
 def maxpool2(x):
     n, h, w, c = x.shape
     y = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=x.device)

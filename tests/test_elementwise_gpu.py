@@ -147,6 +147,33 @@ def test_pool_upsample_backward(cuda_device):
     close_bf16(nchw(ops.sum2x2(nhwc(dout, d))), low.grad)
 
 
+@pytest.mark.parametrize("C,H,W,N", [(128, 16, 24, 2), (64, 8, 8, 3)])
+def test_fused_residual_tail_pool(cuda_device, C, H, W, N):
+    """bn_add_relu_pool2 == maxpool2(bn_add_relu(...)) bit for bit, its argmax points at the first maximum, and
+    maxpool2_bwd_idx == maxpool2_bwd (which recomputes the argmax from the un-pooled tensor)."""
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    d = cuda_device
+    y2, ys = (nhwc(bf(torch.randn(N, C, H, W, generator=g)), d) for _ in range(2))
+
+    def bnp():
+        return torch.stack([torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5]).to(d)
+    b2, bs = bnp(), bnp()
+    out = ops.bn_add_relu(y2, b2, ys, bs)                 # relu -> many exact zeros -> ties inside windows
+    want = ops.maxpool2(out)
+    pooled, idx = ops.bn_add_relu_pool2(y2, b2, ys, bs)
+    assert torch.equal(pooled, want)
+    win = out.view(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(N, H // 2, W // 2, C, 4).float()
+    assert torch.equal(idx.long(), win.argmax(dim=-1).long()) or torch.equal(
+        win.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1), pooled.float())
+    first = (win == win.max(dim=-1, keepdim=True).values).float().argmax(dim=-1)      # first maximum in scan order
+    assert torch.equal(idx.long(), first)
+    dp = nhwc(bf(torch.randn(N, C, H // 2, W // 2, generator=g)), d)
+    a1 = nhwc(bf(torch.randn(N, C, H, W, generator=g)), d)
+    assert torch.equal(ops.maxpool2_bwd_idx(idx, dp), ops.maxpool2_bwd(out, dp))
+    assert torch.equal(ops.maxpool2_bwd_idx(idx, dp, a1, a1), ops.maxpool2_bwd(out, dp, a1, a1))
+
+
 def test_stem_forward_wgrad(cuda_device):
     """7x7 stride-2 stem (hourglass.py:163) = im2col (K=147->192) + 1x1 tcgen05 GEMM; wgrad via the 1x1 wgrad kernel."""
     from real_time_helmet_detection_b200 import ops

@@ -46,23 +46,28 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     __syncthreads();
     const float* pbase = &patch[0][0][0];
     constexpr int kVec = kStemKPad / 8;   // 24 vectors per pixel
-    for (int t = threadIdx.x; t < kTOH * kTOW * kVec; t += blockDim.x) {
-        const int kv = t % kVec, lp = t / kVec;
-        const int lx = lp % kTOW, ly = lp / kTOW;
-        const int oy = oy0 + ly, ox = ox0 + lx;
-        if (oy >= Ho || ox >= Wo) continue;
-        const int pofs = (2 * ly) * (kPW + 1) + 2 * lx;
-        float v[8];
+    // thread -> one FIXED 8-k vector (its 8 patch offsets live in registers) of 10 pixels per pass; 240 of the 256
+    // threads work here. Consecutive threads still write consecutive 16-byte vectors of a pixel's 384-byte row.
+    constexpr int kPixPerPass = 256 / kVec;   // 10
+    const int kv = threadIdx.x % kVec, slot = threadIdx.x / kVec;
+    if (slot < kPixPerPass) {
+        int off[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = koff[kv * 8 + j];
-            v[j] = o >= 0 ? pbase[o + pofs] : 0.f;
+        for (int j = 0; j < 8; ++j) off[j] = koff[kv * 8 + j];
+        for (int lp = slot; lp < kTOH * kTOW; lp += kPixPerPass) {
+            const int lx = lp % kTOW, ly = lp / kTOW;
+            const int oy = oy0 + ly, ox = ox0 + lx;
+            if (oy >= Ho || ox >= Wo) continue;
+            const int pofs = (2 * ly) * (kPW + 1) + 2 * lx;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? pbase[off[j] + pofs] : 0.f;
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * kStemKPad + kv * 8) = u;
         }
-        uint4 u;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * kStemKPad + kv * 8) = u;
     }
 }
 

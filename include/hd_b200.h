@@ -34,6 +34,9 @@ long long hd_launch_count(void);
  * starts with griddepcontrol.launch_dependents / griddepcontrol.wait): 1 = on (default), 0 = off. HD_NO_PDL=1 in the
  * environment also turns it off. */
 void hd_set_pdl(int on);
+/* Profiling aid: with HD_TRACE=1 in the environment every launch is bracketed by timing events; this prints one
+ * "[hd_trace] s<stream> start_ms end_ms duration kernel" row per launch since the last dump to stderr (syncs the device). */
+void hd_trace_dump(void);
 
 /* ------------------------------------------------------------------ convolutions (hourglass.py:94-108) */
 

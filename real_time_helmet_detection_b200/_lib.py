@@ -26,6 +26,7 @@ _SIGNATURES = {
     "hd_version": (I, []),
     "hd_launch_count": (LL, []),
     "hd_set_pdl": (None, [I]),
+    "hd_trace_dump": (None, []),
     "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_igemm_affine": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_bn_fold_all": (I, [P, I, P, P]),

@@ -558,15 +558,17 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 const int ty = (tile / p.tiles_x) % p.tiles_y;
                 const int n = tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * 16, y0 = ty * 16;
-                for (int dx = 0; dx < 3; ++dx) {
+                // 3x3: box of 18 rows per dx, three dy taps inside it; 1x1 (p.kw == 1): one 16-row box, one tap
+                const uint32_t a_bytes = static_cast<uint32_t>(16 + 2 * p.pad) * 16u * 128u;
+                for (int dx = 0; dx < p.kw; ++dx) {
                     for (int ck = 0; ck < p.cin_chunks; ++ck) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
-                        mbar_arrive_expect_tx(&a_full[sa], kHABytes);
-                        tma_load_4d(smem_a + sa * kHABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - 1, y0 - 1, n);
-                        for (int dy = 0; dy < 3; ++dy) {
+                        mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                        tma_load_4d(smem_a + sa * kHABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - p.pad, y0 - p.pad, n);
+                        for (int dy = 0; dy < p.kh; ++dy) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
                             mbar_arrive_expect_tx(&b_full[sb], kHBBytes);
-                            tma_load_3d(smem_b + sb * kHBBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * 3 + dx);
+                            tma_load_3d(smem_b + sb * kHBBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * p.kw + dx);
                             if (++sb == kHBStages) { sb = 0; pb ^= 1; }
                         }
                         if (++sa == kHAStages) { sa = 0; pa ^= 1; }
@@ -582,11 +584,11 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             bool first = true;
-            for (int dx = 0; dx < 3; ++dx) {
+            for (int dx = 0; dx < p.kw; ++dx) {
                 for (int ck = 0; ck < p.cin_chunks; ++ck) {
                     mbar_wait(&a_full[sa], pa);
                     const uint32_t x_addr = smem_u32(smem_a + sa * kHABytes);
-                    for (int dy = 0; dy < 3; ++dy) {
+                    for (int dy = 0; dy < p.kh; ++dy) {
                         mbar_wait(&b_full[sb], pb);
                         tc_fence_after();
                         if (elect_one()) {
@@ -759,13 +761,15 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
         p.bn_count = static_cast<float>(N) * H * W; p.bn_out = bn->out; p.bn_counter = bn->counter;
     }
 
-    // halo variant: 3x3, 128 output channels, map >= 16x16 and enough 16x16 tiles to fill the machine
+    // halo kernel: 3x3 (or 1x1: same kernel, one tap, no halo rows), 128 output channels, map >= 16x16 and enough 16x16
+    // tiles to fill the machine
     bool halo = false;
-    if (ksize == 3 && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 && g_conv_variant != 1) {
+    if ((ksize == 3 || ksize == 1) && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 &&
+        g_conv_variant != 1) {
         const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
         halo = g_conv_variant == 2 || ht >= sm_count();
         if (halo) {
-            tw = 16; th = 18; tn = 1;
+            tw = 16; th = 16 + 2 * p.pad; tn = 1;       // activation box: 16x16 pixels plus the 3x3 halo rows
             p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
             p.num_tiles = ht;
         }

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <vector>
+#include <cstdlib>
 
 namespace hd {
 
@@ -79,6 +81,50 @@ bool pdl_enabled() {
 }
 void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
+// ---------------------------------------------------------------------------------------------- launch trace (HD_TRACE)
+struct TraceRow { const void* func; cudaStream_t stream; cudaEvent_t a, b; };
+static std::vector<TraceRow> g_trace;
+static std::mutex g_trace_mu;
+bool trace_enabled() {
+    static const bool on = getenv("HD_TRACE") != nullptr;
+    return on;
+}
+void trace_begin(const void* func, cudaStream_t stream) {
+    TraceRow r{func, stream, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, stream);
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace.push_back(r);
+}
+void trace_end(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    for (auto it = g_trace.rbegin(); it != g_trace.rend(); ++it)
+        if (it->stream == stream) { cudaEventRecord(it->b, stream); break; }
+}
+void trace_dump() {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    if (g_trace.empty()) return;
+    cudaDeviceSynchronize();
+    std::vector<cudaStream_t> streams;
+    for (auto& r : g_trace) {
+        size_t si = 0;
+        while (si < streams.size() && streams[si] != r.stream) ++si;
+        if (si == streams.size()) streams.push_back(r.stream);
+        float t0 = 0.f, t1 = 0.f;
+        cudaEventElapsedTime(&t0, g_trace.front().a, r.a);
+        cudaEventElapsedTime(&t1, g_trace.front().a, r.b);
+        const char* name = "?";
+        cudaFuncGetName(&name, r.func);
+        fprintf(stderr, "[hd_trace] s%zu %9.3f %9.3f %7.1f us  %s\n", si, t0, t1, (t1 - t0) * 1e3f, name);
+    }
+    for (auto& r : g_trace) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_trace.clear();
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -102,3 +148,5 @@ namespace hd { long long launches(); }
 extern "C" long long hd_launch_count(void) { return hd::launches(); }
 namespace hd { void set_pdl(int on); }
 extern "C" void hd_set_pdl(int on) { hd::set_pdl(on); }
+namespace hd { void trace_dump(); }
+extern "C" void hd_trace_dump(void) { hd::trace_dump(); }

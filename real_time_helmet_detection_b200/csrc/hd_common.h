@@ -60,9 +60,24 @@ struct PdlScope {
 // Exception (launch_k_pdl with early = false): a tensor-core kernel whose grid fills the machine. Its CTAs own a whole
 // SM (200+ KB of shared memory); scheduled early they would sit idle on SMs that the concurrently running weight-
 // gradient kernel of the side stream could use (measured: the train step got 1.3 % slower with PDL on every kernel).
+// HD_TRACE=1: every launch is bracketed by timing events on its stream; hd_trace_dump() prints (stream, start, end,
+// kernel) rows relative to the first launch - a poor man's timeline across the executor's streams (profiling aid only:
+// the events themselves perturb scheduling a little).
+bool trace_enabled();
+void trace_begin(const void* func, cudaStream_t stream);
+void trace_end(cudaStream_t stream);
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k_pdl(bool early, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                 cudaStream_t stream, Args&&... args) {
+    if (trace_enabled()) {
+        trace_begin(reinterpret_cast<const void*>(kernel), stream);
+        cudaLaunchConfig_t c2 = {};
+        c2.gridDim = grid; c2.blockDim = block; c2.dynamicSmemBytes = smem; c2.stream = stream;
+        cudaError_t e = cudaLaunchKernelEx(&c2, kernel, static_cast<Args&&>(args)...);
+        trace_end(stream);
+        return e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -844,8 +844,16 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     HD_REQUIRE(reinterpret_cast<uint8_t*>(workspace) == n->persist.base, "net_backward: workspace moved since the forward pass");
     PdlScope pdl(false);
     n->up = units; n->stream = stream; n->rc = 0;
-    if (!n->side && cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) != cudaSuccess)
-        return fail(HD_ERR_CUDA, "net_backward: cannot create the weight-gradient stream");
+    if (!n->side) {
+        // The weight-gradient stream gets the highest priority: its kernels (wgrad, and above all the tiny split-K
+        // reduce that follows each) share the machine with the main stream's HBM-bound kernels, whose thousands of
+        // queued CTAs otherwise starve them of SM slots (trace: a 12 us wgrad_reduce took 280-470 us at 256x256).
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        static const bool flat = getenv("HD_FLAT_PRIORITY") != nullptr;
+        if (cudaStreamCreateWithPriority(&n->side, cudaStreamNonBlocking, flat ? lo : hi) != cudaSuccess)
+            return fail(HD_ERR_CUDA, "net_backward: cannot create the weight-gradient stream");
+    }
     static const bool serial = getenv("HD_SERIAL_WGRAD") != nullptr;   // debug knob: wgrad on the main stream
     cudaStream_t side_keep = n->side;
     if (serial) n->side = stream;

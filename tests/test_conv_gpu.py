@@ -122,7 +122,7 @@ def test_head_conv(cuda_device):
 
 
 HALO_CASES = [(2, 32, 32, 128, 128, 3), (1, 64, 48, 128, 128, 3), (1, 40, 24, 128, 128, 3), (2, 16, 16, 64, 128, 3),
-              (3, 17, 33, 128, 128, 3)]
+              (3, 17, 33, 128, 128, 3), (2, 32, 32, 128, 128, 1), (2, 16, 48, 64, 128, 1), (1, 40, 24, 128, 128, 1)]
 
 
 @pytest.mark.parametrize("variant", [2])
@@ -137,7 +137,7 @@ def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k, variant):
     r = _bf16_round(torch.randn(N, cout, H, W, generator=g))
     w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5))
     bias = torch.randn(cout, generator=g)
-    conv = F.conv2d(x, w, bias, padding=1)
+    conv = F.conv2d(x, w, bias, padding=(k - 1) // 2)
     ref = conv + r
     _lib.lib().hd_set_conv_variant(variant)
     try:
@@ -147,7 +147,7 @@ def test_conv_halo_variant(cuda_device, N, H, W, cin, cout, k, variant):
         out = ops.to_nchw(y).cpu()
         if cin == cout:
             dy = _bf16_round(torch.randn(N, cout, H, W, generator=g))
-            dref = torch.nn.grad.conv2d_input((N, cin, H, W), w, dy, padding=1)
+            dref = torch.nn.grad.conv2d_input((N, cin, H, W), w, dy, padding=(k - 1) // 2)
             dx = ops.to_nchw(ops.conv2d_igemm(ops.to_nhwc(dy.to(cuda_device)), ops.pack_weight(w.to(cuda_device), mode=1),
                                               cin, k)).cpu()
     finally:

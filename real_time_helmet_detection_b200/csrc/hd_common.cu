@@ -72,7 +72,7 @@ static int g_pdl = -1;
 static thread_local int t_pdl_scope = -1;     // PdlScope override of the calling thread (-1: none)
 int pdl_scope_set(int v) { int old = t_pdl_scope; t_pdl_scope = v; return old; }
 bool pdl_enabled() {
-    if (t_pdl_scope >= 0 && g_pdl != 0) return t_pdl_scope != 0;
+    if (t_pdl_scope >= 0 && g_pdl != 0) return t_pdl_scope != 0;      // scope 2: decided per launch in pdl_allowed()
     if (g_pdl < 0) {
         const char* e = getenv("HD_NO_PDL");
         g_pdl = (e && e[0] == '1') ? 0 : 1;
@@ -80,6 +80,11 @@ bool pdl_enabled() {
     return g_pdl != 0;
 }
 void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+int sm_count();
+bool pdl_allowed(unsigned grid_blocks) {
+    if (!pdl_enabled()) return false;
+    return t_pdl_scope != 2 || grid_blocks < static_cast<unsigned>(sm_count());
+}
 
 // ---------------------------------------------------------------------------------------------- launch trace (HD_TRACE)
 struct TraceRow { const void* func; cudaStream_t stream; cudaEvent_t a, b; };

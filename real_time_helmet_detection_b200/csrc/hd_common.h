@@ -39,14 +39,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int sm_count();
 void count_launch();   // bumps the kernel-launch counter read by hd_launch_count()
 bool pdl_enabled();    // programmatic dependent launch on (default) / off (hd_set_pdl(0) or HD_NO_PDL=1)
+bool pdl_allowed(unsigned grid_blocks);   // ... for a launch of this many CTAs under the calling thread's PdlScope
 int pdl_scope_set(int v);
 // Scoped per-thread override: the training step turns PDL off for its launches. With two execution lanes and the
 // weight-gradient side stream the SMs are already kept busy across kernel boundaries, and early-scheduled CTAs that
 // only wait take slots from the concurrently running kernels (measured: 13.4 ms/step without, 13.7 ms with PDL),
 // while the latency-bound paths - batch-1 inference, decode - gain 7-8 % from it.
+// Mode 2 (the training step): only launches of fewer CTAs than the machine has SMs - the latency-bound kernels of the
+// deep hourglass levels, where the next kernel's early CTAs find idle SMs instead of competing for busy ones.
 struct PdlScope {
     int old;
-    explicit PdlScope(bool on) : old(pdl_scope_set(on ? 1 : 0)) {}
+    explicit PdlScope(int mode) : old(pdl_scope_set(mode)) {}
     ~PdlScope() { pdl_scope_set(old); }
 };
 
@@ -82,7 +85,7 @@ inline cudaError_t launch_k_pdl(bool early, void (*kernel)(KArgs...), dim3 grid,
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = (early && pdl_enabled()) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (early && pdl_allowed(grid.x * grid.y * grid.z)) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
 }

@@ -798,7 +798,9 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
                "net_forward: input (%d,3,%d,%d): H and W must be positive multiples of 64", B, H, W);
     HD_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "net_forward: workspace must be 256-byte aligned");
     size_t head = 0;
-    PdlScope pdl(training == 0);    // see hd_common.h: PDL pays off for the latency-bound eval pass only
+    static const int train_pdl = getenv("HD_TRAIN_PDL") ? atoi(getenv("HD_TRAIN_PDL")) : 0;
+    // see hd_common.h: all launches in eval; training: off (HD_TRAIN_PDL=2 enables it for small grids only - measured neutral)
+    PdlScope pdl(training == 0 ? 1 : train_pdl);
     n->dry = false; n->rc = 0; n->up = units; n->stream = stream;
     {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -842,7 +844,8 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     HD_REQUIRE(n_units == static_cast<int>(n->units.size()), "net_backward: unit table size mismatch");
     HD_REQUIRE(n->trained_fwd, "net_backward: no training-mode forward pass is pending on this network");
     HD_REQUIRE(reinterpret_cast<uint8_t*>(workspace) == n->persist.base, "net_backward: workspace moved since the forward pass");
-    PdlScope pdl(false);
+    static const int train_pdl = getenv("HD_TRAIN_PDL") ? atoi(getenv("HD_TRAIN_PDL")) : 0;
+    PdlScope pdl(train_pdl);
     n->up = units; n->stream = stream; n->rc = 0;
     if (!n->side) {
         // The weight-gradient stream gets the highest priority: its kernels (wgrad, and above all the tiny split-K

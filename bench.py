@@ -242,7 +242,7 @@ def inference_latency(torch, dev, S=1, runs=50):
     from real_time_helmet_detection_b200.hourglass import StackedHourglass
     from real_time_helmet_detection_b200.evaluate import Prediction
     torch.manual_seed(0)
-    net = StackedHourglass(S, 128, 6).to(dev).eval()
+    net = StackedHourglass(S, 128, 6).to(dev).eval().freeze_weights()      # inference: parameters are static
     x = torch.randn(1, 3, 512, 512, device=dev)
     res = {}
     for name, graph in (("eager", False), ("cuda_graph", True)):

@@ -251,6 +251,10 @@ typedef struct hd_net hd_net;
 int hd_net_create(int num_stack, int in_ch, int out_ch, hd_net** net);
 void hd_net_destroy(hd_net* net);
 int hd_net_num_units(const hd_net* net);
+/* Inference with frozen parameters: when on, eval-mode forwards after the next one reuse the packed bf16 weights and
+ * the folded BatchNorm constants in the workspace instead of rebuilding them from the fp32 parameters on every call
+ * (same workspace pointer required; any training-mode forward or a new call of this function invalidates them). */
+void hd_net_set_static_weights(hd_net* net, int on);
 /* Bytes of workspace hd_net_forward (+ hd_net_backward when with_backward) need for a (B,3,H,W) input. */
 size_t hd_net_workspace_bytes(hd_net* net, int B, int H, int W, int with_backward);
 /* StackedHourglass.forward (hourglass.py:223-237): x (B,3,H,W) fp32 -> logits (B,S,out_ch,H/4,W/4) fp32.

@@ -141,6 +141,7 @@ int main(int argc, char** argv) {
             u.num_batches_tracked = nbt;
         }
     }
+    hd_net_set_static_weights(net, 1);      // deployment: weights are packed to bf16 once, on the first forward
     std::printf("model load!\n");
 
     // ---- buffers

@@ -178,3 +178,37 @@ def test_prediction_cuda_graph_matches_eager(cuda_device):
     net.train()
     with pytest.raises(RuntimeError, match="eval"):
         Prediction(net, 50, 4, 0.3, "nms", 0.3, cuda_graph=True)(torch.randn(1, 3, 64, 64, device=cuda_device))
+
+
+def test_freeze_weights_reuses_and_invalidates(cuda_device):
+    """freeze_weights(): eval forwards reuse the packed weights (2 launches fewer) and give identical logits; a change
+    of the parameters is fully picked up once freeze_weights() is called again."""
+    from real_time_helmet_detection_b200 import _lib
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    torch.manual_seed(3)
+    net = StackedHourglass(1, 128, 6).to(cuda_device).eval()
+    x = torch.randn(2, 3, 128, 128, device=cuda_device)
+    L = _lib.lib()
+    with torch.no_grad():
+        ref = net(x)
+        net.freeze_weights()
+        a = net(x)                                   # packs once more
+        n0 = L.hd_launch_count()
+        b = net(x)
+        n_frozen = L.hd_launch_count() - n0
+        net.freeze_weights(False)
+        n0 = L.hd_launch_count()
+        c = net(x)
+        n_plain = L.hd_launch_count() - n0
+        assert torch.equal(ref, a) and torch.equal(ref, b) and torch.equal(ref, c)
+        assert n_plain - n_frozen == 2
+        net.freeze_weights()
+        net(x)
+        for p in net.parameters():
+            p.mul_(1.01)
+        net(x)                                       # contract broken on purpose: a mix of stale packed weights and live biases
+        net.freeze_weights()                         # re-arm after the update
+        fresh = net(x)
+        assert not torch.equal(fresh, ref)
+        net.freeze_weights(False)
+        assert torch.equal(net(x), fresh)

@@ -133,6 +133,11 @@ int hd_bn_act(const void* y, const float* scale, const float* shift, void* z, lo
 /* out = relu(y2*s2 + b2 + skip) with skip = x or ys*ss + bs  (Residual.forward, hourglass.py:125-127) */
 int hd_bn_add_relu(const void* y2, const float* s2, const float* b2, const void* skip, const float* ss,
                    const float* bs, void* out, long long npix, int C, hd_stream_t stream);
+/* Same, additionally storing the ReLU mask of the (bf16-rounded) output as bits: mask_out [npix][C/8] bytes, bit j of
+ * byte v = (out[8v + j] > 0). hd_bn_bwd_reduce_fin_mask / hd_bn_bwd_apply_mask then take that mask instead of re-reading
+ * the activated tensor in the BatchNorm backward of a single-BN residual tail (1 byte instead of 16 per 8 channels). */
+int hd_bn_add_relu_mask(const void* y2, const float* s2, const float* b2, const void* skip, const float* ss,
+                        const float* bs, void* out, void* mask_out, long long npix, int C, hd_stream_t stream);
 int hd_maxpool2(const void* x, void* y, int N, int H, int W, int C, hd_stream_t stream);           /* :72  */
 int hd_upsample2_add(const void* up1, const void* low, void* out, int N, int H, int W, int C,
                      hd_stream_t stream);                                                         /* :147,:156 */
@@ -158,6 +163,10 @@ typedef struct hd_bn_bwd_fuse {
 int hd_bn_bwd_reduce_fin(const void* dout, const void* out, const float* act_scale, const float* act_shift,
                          const float* act_scale_s, const float* act_shift_s, const void* y, const void* ys,
                          float* sums, long long npix, int C, const hd_bn_bwd_fuse* fin, hd_stream_t stream);
+int hd_bn_bwd_reduce_fin_mask(const void* dout, const void* mask, const void* y, float* sums, long long npix, int C,
+                              const hd_bn_bwd_fuse* fin, hd_stream_t stream);
+int hd_bn_bwd_apply_mask(const void* dout, const void* mask, const void* y, const float* coef, void* dy, void* gout,
+                         long long npix, int C, hd_stream_t stream);
 int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
                        const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
                        hd_stream_t stream);

@@ -44,6 +44,9 @@ _SIGNATURES = {
     "hd_bn_finalize": (I, [P, P, F, P, P, P, P, P, F, F, I, P, P, P, P, I, P]),
     "hd_bn_act": (I, [P, P, P, P, LL, I, I, P]),
     "hd_bn_add_relu": (I, [P, P, P, P, P, P, P, LL, I, P]),
+    "hd_bn_add_relu_mask": (I, [P, P, P, P, P, P, P, P, LL, I, P]),
+    "hd_bn_bwd_reduce_fin_mask": (I, [P, P, P, P, LL, I, P, P]),
+    "hd_bn_bwd_apply_mask": (I, [P, P, P, P, P, P, LL, I, P]),
     "hd_maxpool2": (I, [P, P, I, I, I, I, P]),
     "hd_upsample2_add": (I, [P, P, P, I, I, I, I, P]),
     "hd_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),

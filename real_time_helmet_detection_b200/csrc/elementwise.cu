@@ -120,7 +120,7 @@ template <bool SKIP_BN>
 __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ s2,
                                    const float* __restrict__ b2, const __nv_bfloat16* __restrict__ skip,
                                    const float* __restrict__ ss, const float* __restrict__ bs,
-                                   __nv_bfloat16* __restrict__ out, size_t nvec, int C) {
+                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, size_t nvec, int C) {
     pdl_prologue();
     __shared__ __align__(16) float p[4][256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -147,6 +147,12 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
             a.v[j] = fmaxf(t + sv, 0.f);
         }
         store8(out + i * 8, a);
+        if (mask) {     // ReLU mask of the STORED (bf16-rounded) output, one bit per channel: backward reads 1 byte, not 16
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m |= (__bfloat162float(__float2bfloat16_rn(a.v[j])) > 0.f ? 1u : 0u) << j;
+            mask[i] = static_cast<uint8_t>(m);
+        }
     }
 }
 
@@ -295,7 +301,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                      const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
-                     float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin) {
+                     float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin,
+                     const uint8_t* __restrict__ mbits) {
     pdl_prologue();
     extern __shared__ __align__(16) float red[];  // [3][C]
     const int cvec = C >> 3;
@@ -323,7 +330,15 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         F8 g = load8(dout + off);
         F8 yy = load8(y + off);
         F8 o, y2;
-        if (!REMASK) o = load8(out + off);
+        if (!REMASK) {
+            if (mbits) {        // stored ReLU mask bits (bn_add_relu_kernel) instead of the activated tensor
+                const uint32_t m = mbits[off >> 3];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = static_cast<float>((m >> j) & 1u);
+            } else {
+                o = load8(out + off);
+            }
+        }
         if (SECOND) y2 = load8(ys + off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -427,10 +442,11 @@ __global__ void __launch_bounds__(256, SECOND ? 2 : 4) bn_bwd_apply_kernel(const
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ys,
                                     const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dys,
-                                    __nv_bfloat16* __restrict__ gout, size_t nvec, int C) {
+                                    __nv_bfloat16* __restrict__ gout, size_t nvec, int C,
+                                    const uint8_t* __restrict__ mbits) {
     pdl_prologue();
     __shared__ __align__(16) float p[10][256];
-    const bool remask = out == nullptr;
+    const bool remask = out == nullptr && mbits == nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         p[6][i] = remask ? act_scale[i] : 0.f;
         p[7][i] = remask ? act_shift[i] : 0.f;
@@ -469,6 +485,10 @@ __global__ void __launch_bounds__(256, SECOND ? 2 : 4) bn_bwd_apply_kernel(const
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o.v[j] += fmaf(y2.v[j], asc[j], ash[j]);
             }
+        } else if (mbits) {
+            const uint32_t m = mbits[i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = static_cast<float>((m >> j) & 1u);
         } else {
             o = load8(out + i * 8);
         }
@@ -643,18 +663,24 @@ extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z,
     return HD_OK;
 }
 
-extern "C" int hd_bn_add_relu(cvp y2, const float* s2, const float* b2, cvp skip, const float* ss, const float* bs,
-                              void* out, long long npix, int C, cudaStream_t stream) {
+extern "C" int hd_bn_add_relu_mask(cvp y2, const float* s2, const float* b2, cvp skip, const float* ss, const float* bs,
+                                   void* out, void* mask_out, long long npix, int C, cudaStream_t stream) {
+    uint8_t* mask = reinterpret_cast<uint8_t*>(mask_out);
     HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_add_relu: C=%d", C);
     HD_REQUIRE((ss == nullptr) == (bs == nullptr), "bn_add_relu: skip scale/shift must come in pairs");
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (ss)
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
+}
+
+extern "C" int hd_bn_add_relu(cvp y2, const float* s2, const float* b2, cvp skip, const float* ss, const float* bs,
+                              void* out, long long npix, int C, cudaStream_t stream) {
+    return hd_bn_add_relu_mask(y2, s2, b2, skip, ss, bs, out, nullptr, npix, C, stream);
 }
 
 extern "C" int hd_maxpool2(cvp x, void* y, int N, int H, int W, int C, cudaStream_t stream) {
@@ -683,9 +709,27 @@ extern "C" int hd_bn_bwd_reduce(cvp dout, cvp out, const float* act_scale, const
     return hd_bn_bwd_reduce_fin(dout, out, act_scale, act_shift, nullptr, nullptr, y, ys, sums, npix, C, nullptr, stream);
 }
 
+static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const float* act_scale, const float* act_shift,
+                              const float* act_scale_s, const float* act_shift_s, cvp y, cvp ys, float* sums,
+                              long long npix, int C, const hd_bn_bwd_fuse* fin_in, cudaStream_t stream);
+
 extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, const float* act_shift,
                                     const float* act_scale_s, const float* act_shift_s, cvp y, cvp ys, float* sums,
                                     long long npix, int C, const hd_bn_bwd_fuse* fin_in, cudaStream_t stream) {
+    return bn_bwd_reduce_impl(dout, out, nullptr, act_scale, act_shift, act_scale_s, act_shift_s, y, ys, sums, npix, C,
+                              fin_in, stream);
+}
+
+extern "C" int hd_bn_bwd_reduce_fin_mask(cvp dout, cvp mask, cvp y, float* sums, long long npix, int C,
+                                         const hd_bn_bwd_fuse* fin_in, cudaStream_t stream) {
+    HD_REQUIRE(mask != nullptr, "bn_bwd_reduce_fin_mask: null mask");
+    return bn_bwd_reduce_impl(dout, nullptr, reinterpret_cast<const uint8_t*>(mask), nullptr, nullptr, nullptr, nullptr, y,
+                              nullptr, sums, npix, C, fin_in, stream);
+}
+
+static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const float* act_scale, const float* act_shift,
+                              const float* act_scale_s, const float* act_shift_s, cvp y, cvp ys, float* sums,
+                              long long npix, int C, const hd_bn_bwd_fuse* fin_in, cudaStream_t stream) {
     hd_bn_bwd_fuse fin{};
     if (fin_in) fin = *fin_in;
     HD_REQUIRE(fin.coef == nullptr || (fin.counter && fin.gamma && fin.mean && fin.rstd && fin.count > 0.f),
@@ -693,22 +737,26 @@ extern "C" int hd_bn_bwd_reduce_fin(cvp dout, cvp out, const float* act_scale, c
     HD_REQUIRE(fin.coef == nullptr || ys == nullptr || (fin.coef_s && fin.gamma_s && fin.mean_s && fin.rstd_s),
                "bn_bwd_reduce: fused finalize of the skip branch needs its gamma / mean / rstd / coef");
     HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_reduce: C=%d", C);
-    HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_reduce: need `out` or the activation scale/shift");
-    HD_REQUIRE(out != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
+    HD_REQUIRE(out != nullptr || mbits != nullptr || (act_scale && act_shift),
+               "bn_bwd_reduce: need `out`, mask bits or the activation scale/shift");
+    HD_REQUIRE(out != nullptr || mbits != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
                "bn_bwd_reduce: rebuilding the mask of a two-branch tail needs the skip branch's scale/shift too");
+    HD_REQUIRE(mbits == nullptr || ys == nullptr, "bn_bwd_reduce: mask bits are for single-BN tails");
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
-    if (ys && out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin));
+    if (mbits)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, mbits));
+    else if (ys && out)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
     else if (out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -722,25 +770,46 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
     return HD_OK;
 }
 
+static int bn_bwd_apply_impl(cvp dout, cvp out, const uint8_t* mbits, const float* act_scale, const float* act_shift,
+                             const float* act_scale_s, const float* act_shift_s, cvp y, const float* coef, void* dy,
+                             cvp ys, const float* coef_s, void* dys, void* gout, long long npix, int C,
+                             cudaStream_t stream);
+
 extern "C" int hd_bn_bwd_apply(cvp dout, cvp out, const float* act_scale, const float* act_shift,
                                const float* act_scale_s, const float* act_shift_s, cvp y, const float* coef, void* dy,
                                cvp ys, const float* coef_s, void* dys, void* gout, long long npix, int C,
                                cudaStream_t stream) {
+    return bn_bwd_apply_impl(dout, out, nullptr, act_scale, act_shift, act_scale_s, act_shift_s, y, coef, dy, ys, coef_s,
+                             dys, gout, npix, C, stream);
+}
+
+extern "C" int hd_bn_bwd_apply_mask(cvp dout, cvp mask, cvp y, const float* coef, void* dy, void* gout, long long npix,
+                                    int C, cudaStream_t stream) {
+    HD_REQUIRE(mask != nullptr, "bn_bwd_apply_mask: null mask");
+    return bn_bwd_apply_impl(dout, nullptr, reinterpret_cast<const uint8_t*>(mask), nullptr, nullptr, nullptr, nullptr, y,
+                             coef, dy, nullptr, nullptr, nullptr, gout, npix, C, stream);
+}
+
+static int bn_bwd_apply_impl(cvp dout, cvp out, const uint8_t* mbits, const float* act_scale, const float* act_shift,
+                             const float* act_scale_s, const float* act_shift_s, cvp y, const float* coef, void* dy,
+                             cvp ys, const float* coef_s, void* dys, void* gout, long long npix, int C,
+                             cudaStream_t stream) {
     HD_REQUIRE(C % 8 == 0 && C <= 256, "bn_bwd_apply: C=%d", C);
-    HD_REQUIRE(out != nullptr || (act_scale && act_shift), "bn_bwd_apply: need `out` or the activation scale/shift");
-    HD_REQUIRE(out != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
+    HD_REQUIRE(out != nullptr || mbits != nullptr || (act_scale && act_shift),
+               "bn_bwd_apply: need `out`, mask bits or the activation scale/shift");
+    HD_REQUIRE(out != nullptr || mbits != nullptr || ys == nullptr || (act_scale_s && act_shift_s),
                "bn_bwd_apply: rebuilding the mask of a two-branch tail needs the skip branch's scale/shift too");
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
     if (ys && gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C, mbits));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C, mbits));
     else if (gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C, mbits));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C, mbits));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

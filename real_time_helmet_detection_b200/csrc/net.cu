@@ -43,6 +43,7 @@ struct Unit {
 struct ResSaved {
     int u1, u2, us;  // unit ids (us = -1: identity skip)
     bf16 *X, *Y1, *Z1, *Y2, *Ys, *Out;
+    uint8_t* Mask;   // training, identity skip: ReLU mask bits of Out (1 bit per element) for the BatchNorm backward
     int H, W, cin, cout;
 };
 
@@ -419,6 +420,9 @@ static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int t
     r.Y2 = reinterpret_cast<bf16*>(n->fw.alloc(bytes));
     r.Ys = r.us >= 0 ? reinterpret_cast<bf16*>(n->fw.alloc(bytes)) : nullptr;
     r.Out = pooled ? nullptr : reinterpret_cast<bf16*>(n->fw.alloc(bytes));
+    static const bool no_mask = getenv("HD_NO_MASK_BITS") != nullptr;
+    r.Mask = (training && r.us < 0 && !no_mask) ? reinterpret_cast<uint8_t*>(n->fw.alloc(static_cast<size_t>(npix) * r.cout / 8))
+                                                 : nullptr;
     Unit &u1 = n->units[r.u1], &u2 = n->units[r.u2];
     if (!training) {
         // relu(bn1(conv1)) -> Z1 ; [bn_s(conv_s) -> Ys] ; relu(bn2(conv2) + skip) -> Out : 2-3 launches
@@ -445,7 +449,8 @@ static bf16* residual_fwd(hd_net* n, int ri, bf16* X, int B, int H, int W, int t
         RUN(hd_bn_add_relu(r.Y2, u2.bnp, u2.bnp + u2.cout, r.Ys, us.bnp, us.bnp + us.cout, r.Out, npix, r.cout,
                            n->stream));
     } else {
-        RUN(hd_bn_add_relu(r.Y2, u2.bnp, u2.bnp + u2.cout, X, nullptr, nullptr, r.Out, npix, r.cout, n->stream));
+        RUN(hd_bn_add_relu_mask(r.Y2, u2.bnp, u2.bnp + u2.cout, X, nullptr, nullptr, r.Out, r.Mask, npix, r.cout,
+                                n->stream));
     }
     return r.Out;
 }
@@ -580,7 +585,7 @@ static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H
 
 // BN (+ReLU) backward of one unit: g = dout * (out > 0) -> dy (and the skip branch / g when requested)
 static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, const bf16* y, bf16* dy, int us,
-                        const bf16* ys, bf16* dys, bf16* gout) {
+                        const bf16* ys, bf16* dys, bf16* gout, const uint8_t* mask = nullptr) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
     const int C = u.cout;
@@ -606,6 +611,11 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
     // instead of reading the stored block output (saves a 537 MB read per kernel at 256x256)
     const float* sc_s = s ? s->bnp : nullptr;
     const float* sh_s = s ? s->bnp + C : nullptr;
+    if (mask && !s) {     // single-BN residual tail with stored ReLU mask bits: `out` is not read at all
+        RUN(hd_bn_bwd_reduce_fin_mask(dout, mask, y, sums, u.npix, C, &fin, n->stream));
+        RUN(hd_bn_bwd_apply_mask(dout, mask, y, coef, dy, gout, u.npix, C, n->stream));
+        return;
+    }
     const bf16* mask_src = s ? nullptr : out;
     RUN(hd_bn_bwd_reduce_fin(dout, mask_src, u.bnp, u.bnp + C, sc_s, sh_s, y, ys, sums, u.npix, C, &fin, n->stream));
     RUN(hd_bn_bwd_apply(dout, mask_src, u.bnp, u.bnp + C, sc_s, sh_s, y, coef, dy, ys, s ? coef_s : nullptr, dys, gout,
@@ -622,7 +632,7 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     bf16* dYs = r.us >= 0 ? reinterpret_cast<bf16*>(n->wg.alloc(bytes_o)) : nullptr;
     bf16* dY1 = reinterpret_cast<bf16*>(n->wg.alloc(bytes_o));
     bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
-    bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G);
+    bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G, r.Mask);
     bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
     // The readiness event is recorded AFTER the dgrad launch on purpose: dgrad and wgrad are both persistent

@@ -174,6 +174,43 @@ def test_fused_residual_tail_pool(cuda_device, C, H, W, N):
     assert torch.equal(ops.maxpool2_bwd_idx(idx, dp, a1, a1), ops.maxpool2_bwd(out, dp, a1, a1))
 
 
+def test_relu_mask_bits_path(cuda_device):
+    """bn_add_relu_mask stores (out > 0) as bits; BN backward from the bits == BN backward from the activated tensor."""
+    import ctypes
+    from real_time_helmet_detection_b200 import ops, _lib
+    g = torch.Generator().manual_seed(8)
+    d = cuda_device
+    N, C, H, W = 2, 128, 16, 12
+    y2, x = (nhwc(bf(torch.randn(N, C, H, W, generator=g)), d) for _ in range(2))
+    b2 = torch.stack([torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5, torch.randn(C, generator=g) * 0.1,
+                      torch.rand(C, generator=g) + 0.5]).to(d)                      # scale | shift | mean | rstd
+    out = torch.empty_like(y2)
+    mask = torch.zeros(N * H * W * C // 8, dtype=torch.uint8, device=d)
+    L = _lib.lib()
+    npix = N * H * W
+    _lib.check(L.hd_bn_add_relu_mask(_lib.ptr(y2), _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(x), None, None, _lib.ptr(out),
+                                     _lib.ptr(mask), npix, C, _lib.stream()))
+    assert torch.equal(out, ops.bn_add_relu(y2, b2, x))
+    bits = ((mask.view(-1, 1).int() >> torch.arange(8, device=d).view(1, 8)) & 1).bool().view(N, H, W, C)
+    assert torch.equal(bits, out.float() > 0)
+    dout = nhwc(bf(torch.randn(N, C, H, W, generator=g)), d)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(d)
+    ref = ops.bn_bwd(dout, out, y2, b2, gamma, want_g=True)
+    sums = torch.zeros(3, C, device=d)
+    _lib.check(L.hd_bn_bwd_reduce_fin_mask(_lib.ptr(dout), _lib.ptr(mask), _lib.ptr(y2), _lib.ptr(sums), npix, C, None,
+                                           _lib.stream()))
+    coef, dgm, dbt = torch.empty(3, C, device=d), torch.empty(C, device=d), torch.empty(C, device=d)
+    _lib.check(L.hd_bn_bwd_finalize(_lib.ptr(sums[0]), _lib.ptr(sums[1]), float(npix), _lib.ptr(gamma), _lib.ptr(b2[2]),
+                                    _lib.ptr(b2[3]), _lib.ptr(coef), _lib.ptr(dgm), _lib.ptr(dbt), 0, C, _lib.stream()))
+    dy, gout = torch.empty_like(y2), torch.empty_like(y2)
+    _lib.check(L.hd_bn_bwd_apply_mask(_lib.ptr(dout), _lib.ptr(mask), _lib.ptr(y2), _lib.ptr(coef), _lib.ptr(dy),
+                                      _lib.ptr(gout), npix, C, _lib.stream()))
+    assert torch.equal(gout, ref[2])
+    # the per-channel sums come from fp32 atomics (order varies run to run): dy may differ in the last bf16 bit
+    assert (dy.float() - ref[0].float()).abs().max() <= 2 ** -7 * ref[0].float().abs().max()
+    assert torch.allclose(dgm, ref[3][0], rtol=1e-5, atol=1e-5) and torch.allclose(dbt, ref[3][1], rtol=1e-5, atol=1e-5)
+
+
 def test_stem_forward_wgrad(cuda_device):
     """7x7 stride-2 stem (hourglass.py:163) = im2col (K=147->192) + 1x1 tcgen05 GEMM; wgrad via the 1x1 wgrad kernel."""
     from real_time_helmet_detection_b200 import ops

@@ -212,3 +212,39 @@ def test_freeze_weights_reuses_and_invalidates(cuda_device):
         assert not torch.equal(fresh, ref)
         net.freeze_weights(False)
         assert torch.equal(net(x), fresh)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 192, 320), (1, 64, 64), (5, 128, 64)])
+def test_ragged_shapes_train_and_eval(cuda_device, B, H, W):
+    """Odd batch sizes and non-square inputs (any H, W that are multiples of 64): the train step matches the bf16-emulating
+    oracle's loss, every gradient is finite, and the eval forward agrees with the oracle's eval forward."""
+    from oracle import hourglass_ref, loss_ref
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.loss import LossCalculator
+    from real_time_helmet_detection_b200.train import train_step
+    torch.manual_seed(B * 7 + H)
+    net = StackedHourglass(1, 128, 6)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, H, W, generator=g)
+    h, w = H // 4, W // 4
+    ghm = torch.rand(B, 2, h, w, generator=g) ** 8
+    mask = (torch.rand(B, 1, h, w, generator=g) > 0.97).float()
+    ghm = torch.maximum(ghm, mask.expand(-1, 2, -1, -1) * (torch.rand(B, 2, h, w, generator=g) > 0.5))
+    goff, gsz = torch.rand(B, 2, h, w, generator=g) * mask, torch.rand(B, 2, h, w, generator=g) * 8 * mask
+    net = net.to(cuda_device).train()
+    crit = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0)
+    loss = train_step(net, crit, x.to(cuda_device), ghm.to(cuda_device), goff.to(cuda_device), gsz.to(cuda_device),
+                      mask.to(cuda_device))
+    ref_out = hourglass_ref.stacked_hourglass_forward(sd, x, training=True, emulate_bf16=True)
+    ref_loss = loss_ref.losses_from_logits(ref_out[:, 0], ghm, goff, gsz, mask)[3]
+    assert abs(float(loss) - float(ref_loss)) <= 5e-3 * abs(float(ref_loss)) + 1e-3, (float(loss), float(ref_loss))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    net.eval()
+    with torch.no_grad():
+        out = net(x.to(cuda_device)).cpu()
+    sd_after = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref_eval = hourglass_ref.stacked_hourglass_forward(sd_after, x, training=False, emulate_bf16=True)
+    assert out.shape == (B, 1, 6, h, w)
+    rel = (out - ref_eval).norm() / ref_eval.norm()
+    assert rel <= 6e-2, float(rel)

@@ -402,7 +402,8 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_kernel<BLOCK_N>, grid, BLOCK_N >= 64 ? 384 : kThreads,
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_kernel<BLOCK_N>, grid,
+                                     BLOCK_N >= 64 ? 384 : kThreads,
                                      smem_bytes, stream, tx, tw, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
@@ -672,7 +673,8 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
     int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle128=*/false);
     if (rc) return rc;
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes, stream, tx, tw,
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes,
+                                     stream, tx, tw,
                                      to, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;

@@ -255,7 +255,8 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set = true;
     }
-    HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HALO>, p.groups * p.ksplit,
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HALO>,
+                                     p.groups * p.ksplit,
                                      kWgThreads, smem_bytes, stream, tdy, tx, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
@@ -329,7 +330,8 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
                             : (halo ? launch_wgrad<64, true>(tdy, tx, p, stream) : launch_wgrad<64, false>(tdy, tx, p, stream));
     if (rc) return rc;
     const int total = p.taps * cout * cin_real;
-    HD_CHECK_CUDA(::hd::launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, p.ws, grad_w, p.ksplit, p.taps, cout, cin_real, 128, cin, accumulate, stem_perm));
+    HD_CHECK_CUDA(::hd::launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, p.ws, grad_w, p.ksplit,
+                                 p.taps, cout, cin_real, 128, cin, accumulate, stem_perm));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

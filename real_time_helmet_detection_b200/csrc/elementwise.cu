@@ -645,7 +645,9 @@ extern "C" int hd_bn_finalize(const float* sum, const float* sqsum, float count,
                               float* shift, float* save_mean, float* save_rstd, int C, cudaStream_t stream) {
     HD_REQUIRE(C > 0 && C <= 256, "bn_finalize: C=%d", C);
     HD_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
-    HD_CHECK_CUDA(::hd::launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, stream, sum, sqsum, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_rstd, C));
+    HD_CHECK_CUDA(::hd::launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, stream, sum, sqsum, count, gamma, beta,
+                                 running_mean, running_var, num_batches_tracked, momentum, eps, training, scale, shift,
+                                 save_mean, save_rstd, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -656,9 +658,11 @@ extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z,
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (relu)
-        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z),
+                                     nvec, C));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z), nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z),
+                                     nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -671,9 +675,11 @@ extern "C" int hd_bn_add_relu_mask(cvp y2, const float* s2, const float* b2, cvp
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (ss)
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2,
+                                     BF(skip), ss, bs, BFW(out), mask, nvec, C));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2,
+                                     BF(skip), ss, bs, BFW(out), mask, nvec, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -696,7 +702,8 @@ extern "C" int hd_upsample2_add(cvp up1, cvp low, void* out, int N, int H, int W
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "upsample2_add: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * H * W * (C / 8);
     if (nvec == 0) return HD_OK;
-    HD_CHECK_CUDA(::hd::launch_k(upsample_add_kernel, ew_blocks(nvec), 256, 0, stream, BF(up1), BF(low), BFW(out), N, H, W, C));
+    HD_CHECK_CUDA(::hd::launch_k(upsample_add_kernel, ew_blocks(nvec), 256, 0, stream, BF(up1), BF(low), BFW(out), N, H,
+                                 W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -748,15 +755,25 @@ static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const flo
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
     if (mbits)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, mbits));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), nullptr,
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     mbits));
     else if (ys && out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr,
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
     else if (out)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr, act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, static_cast<const uint8_t*>(nullptr)));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr,
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -765,7 +782,8 @@ extern "C" int hd_bn_bwd_finalize(const float* s0, const float* s1, float count,
                                   const float* mean, const float* rstd, float* coef, float* dgamma, float* dbeta,
                                   int accumulate, int C, cudaStream_t stream) {
     HD_REQUIRE(C > 0 && C <= 256, "bn_bwd_finalize: C=%d", C);
-    HD_CHECK_CUDA(::hd::launch_k(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, stream, s0, s1, count, gamma, mean, rstd, coef, dgamma, dbeta, accumulate, C));
+    HD_CHECK_CUDA(::hd::launch_k(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, stream, s0, s1, count, gamma, mean,
+                                 rstd, coef, dgamma, dbeta, accumulate, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -803,13 +821,21 @@ static int bn_bwd_apply_impl(cvp dout, cvp out, const uint8_t* mbits, const floa
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
     if (ys && gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), BFW(gout), nvec, C, mbits));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys),
+                                     coef_s, BFW(dys), BFW(gout), nvec, C, mbits));
     else if (ys)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys), coef_s, BFW(dys), nullptr, nvec, C, mbits));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, false>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys),
+                                     coef_s, BFW(dys), nullptr, nvec, C, mbits));
     else if (gout)
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, BFW(gout), nvec, C, mbits));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr,
+                                     nullptr, nullptr, BFW(gout), nvec, C, mbits));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr, nullptr, nvec, C, mbits));
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr,
+                                     nullptr, nullptr, nullptr, nvec, C, mbits));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -819,7 +845,8 @@ extern "C" int hd_maxpool2_bwd(cvp x, cvp dpool, cvp add1, cvp add2, void* dx, i
     HD_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: shape (%d,%d,%d,%d)", N, H, W, C);
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
-    HD_CHECK_CUDA(::hd::launch_k(maxpool2_bwd_kernel, ew_blocks(nvec), 256, 0, stream, BF(x), BF(dpool), BF(add1), BF(add2), BFW(dx), N, H, W, C));
+    HD_CHECK_CUDA(::hd::launch_k(maxpool2_bwd_kernel, ew_blocks(nvec), 256, 0, stream, BF(x), BF(dpool), BF(add1),
+                                 BF(add2), BFW(dx), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -831,7 +858,8 @@ extern "C" int hd_bn_add_relu_pool2(cvp y2, const float* s2, const float* b2, cv
     HD_REQUIRE(y2 && ys && s2 && b2 && ss && bs && pooled && idx, "bn_add_relu_pool2: null argument");
     const size_t nvec = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
     if (nvec == 0) return HD_OK;
-    HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_pool_kernel, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(ys), ss, bs,
+    HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_pool_kernel, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(ys), ss,
+                                 bs,
                                  BFW(pooled), reinterpret_cast<uint8_t*>(idx), N, H, W, C));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
@@ -871,7 +899,8 @@ extern "C" int hd_colsum(cvp x, float* out, long long npix, int C, int cs, cudaS
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 4);
-    HD_CHECK_CUDA(::hd::launch_k(colsum_kernel, blocks, 256, static_cast<size_t>(C) * sizeof(float), stream, BF(x), out, static_cast<size_t>(npix), C, cs));
+    HD_CHECK_CUDA(::hd::launch_k(colsum_kernel, blocks, 256, static_cast<size_t>(C) * sizeof(float), stream, BF(x), out,
+                                 static_cast<size_t>(npix), C, cs));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -901,7 +930,8 @@ extern "C" int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, 
     if (jobs_host)
         HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(BnFoldJob),
                                       cudaMemcpyHostToDevice, stream));
-    HD_CHECK_CUDA(::hd::launch_k(bn_fold_all_kernel, njobs, 128, 0, stream, reinterpret_cast<const BnFoldJob*>(jobs_dev)));
+    HD_CHECK_CUDA(::hd::launch_k(bn_fold_all_kernel, njobs, 128, 0, stream,
+                                 reinterpret_cast<const BnFoldJob*>(jobs_dev)));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -145,7 +145,8 @@ extern "C" int hd_encode_targets(const float* boxes, const int* labels, int B, i
     HD_REQUIRE(scale_factor >= 1, "encode_targets: scale_factor=%d", scale_factor);
     HD_REQUIRE(heat && offset && size && mask && (nmax == 0 || (boxes && labels)), "encode_targets: null pointer");
     dim3 grid((h * w + 255) / 256, B);
-    HD_CHECK_CUDA(::hd::launch_k(encode_targets_kernel, grid, 256, 0, stream, boxes, labels, nmax, h, w, num_cls, scale_factor, normalized, heat, offset, size, mask, err_count));
+    HD_CHECK_CUDA(::hd::launch_k(encode_targets_kernel, grid, 256, 0, stream, boxes, labels, nmax, h, w, num_cls,
+                                 scale_factor, normalized, heat, offset, size, mask, err_count));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -161,7 +162,9 @@ extern "C" int hd_normalize_u8(const void* img_nhwc_u8, float* out_nchw, int B, 
                "normalize_u8: pointers must be 4 / 16 byte aligned");
     const long long quads = static_cast<long long>(H) * W / 4;
     dim3 grid(static_cast<unsigned>((quads + 255) / 256), B);
-    HD_CHECK_CUDA(::hd::launch_k(normalize_u8_kernel, grid, 256, 0, stream, reinterpret_cast<const uint32_t*>(img_nhwc_u8), out_nchw, quads, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]));
+    HD_CHECK_CUDA(::hd::launch_k(normalize_u8_kernel, grid, 256, 0, stream,
+                                 reinterpret_cast<const uint32_t*>(img_nhwc_u8), out_nchw, quads, mean3[0], mean3[1],
+                                 mean3[2], std3[0], std3[1], std3[2]));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

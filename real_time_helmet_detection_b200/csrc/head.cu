@@ -137,11 +137,23 @@ extern "C" int hd_head_backward(const float* dlogits, long long bs, const void* 
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     if (cout <= 6)
-        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<6>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<6>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W,
+                                     cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+                                     reinterpret_cast<const __nv_bfloat16*>(feat),
+                                     reinterpret_cast<const __nv_bfloat16*>(wp),
+                                     reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     else if (cout <= 8)
-        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<8>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<8>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W,
+                                     cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+                                     reinterpret_cast<const __nv_bfloat16*>(feat),
+                                     reinterpret_cast<const __nv_bfloat16*>(wp),
+                                     reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     else
-        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<16>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W, cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs, reinterpret_cast<const __nv_bfloat16*>(feat), reinterpret_cast<const __nv_bfloat16*>(wp), reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
+        HD_CHECK_CUDA(::hd::launch_k(head_bwd_kernel<16>, static_cast<unsigned>(g), 256, 0, stream,  dlogits, bs, H * W,
+                                     cout, reinterpret_cast<const __nv_bfloat16*>(extra), extra_cs,
+                                     reinterpret_cast<const __nv_bfloat16*>(feat),
+                                     reinterpret_cast<const __nv_bfloat16*>(wp),
+                                     reinterpret_cast<__nv_bfloat16*>(dfeat), dw, dbias, npix));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -193,9 +193,11 @@ extern "C" int hd_loss_forward(const float* hm, long long hm_bs, const float* of
                        from_logits, sigmoid_reg);
     if (rc) return rc;
     HD_CHECK_CUDA(cudaMemsetAsync(sums, 0, 5 * sizeof(float), stream));
-    HD_CHECK_CUDA(::hd::launch_k(loss_fwd_kernel, loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream, a, sums));
+    HD_CHECK_CUDA(::hd::launch_k(loss_fwd_kernel, loss_grid(static_cast<long long>(B) * H * W), 256, 0, stream, a,
+                                 sums));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
-    HD_CHECK_CUDA(::hd::launch_k(loss_finalize_kernel, 1, 1, 0, stream, sums, out, static_cast<float>(B), w_hm, w_off, w_size));
+    HD_CHECK_CUDA(::hd::launch_k(loss_finalize_kernel, 1, 1, 0, stream, sums, out, static_cast<float>(B), w_hm, w_off,
+                                 w_size));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

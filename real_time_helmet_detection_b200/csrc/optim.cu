@@ -71,7 +71,9 @@ extern "C" int hd_adam_step(const void* jobs_host, int njobs, void* jobs_dev, lo
     HD_REQUIRE(nchunks < (1ll << 31), "adam_step: too many chunks");
     HD_CHECK_CUDA(cudaMemcpyAsync(jobs_dev, jobs_host, static_cast<size_t>(njobs) * sizeof(AdamJob),
                                   cudaMemcpyHostToDevice, stream));
-    HD_CHECK_CUDA(::hd::launch_k(adam_multi_kernel, static_cast<unsigned>(nchunks), 256, 0, stream,  reinterpret_cast<const AdamJob*>(jobs_dev), njobs, nchunks, lr, beta1, beta2, eps, step_dev, grad_scale, found_inf));
+    HD_CHECK_CUDA(::hd::launch_k(adam_multi_kernel, static_cast<unsigned>(nchunks), 256, 0, stream,
+                                  reinterpret_cast<const AdamJob*>(jobs_dev), njobs, nchunks, lr, beta1, beta2, eps,
+                                 step_dev, grad_scale, found_inf));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     HD_CHECK_CUDA(::hd::launch_k(adam_advance_step_kernel, 1, 1, 0, stream, step_dev, found_inf));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();

@@ -99,7 +99,8 @@ extern "C" int hd_pack_all_weights(const void* jobs, int njobs, long long total,
     HD_REQUIRE(njobs > 0 && total > 0, "pack_all_weights: empty job table");
     const long long blocks = (total + 255) / 256;
     HD_REQUIRE(blocks < (1ll << 31), "pack_all_weights: too many elements");
-    HD_CHECK_CUDA(::hd::launch_k(pack_all_kernel, static_cast<unsigned>(blocks), 256, 0, stream, reinterpret_cast<const PackJob*>(jobs), njobs, total));
+    HD_CHECK_CUDA(::hd::launch_k(pack_all_kernel, static_cast<unsigned>(blocks), 256, 0, stream,
+                                 reinterpret_cast<const PackJob*>(jobs), njobs, total));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -111,7 +112,9 @@ extern "C" int hd_pack_conv_weight(const float* w_oihw, void* out, int cout, int
     const int rows = mode == 0 ? cout : cin, kdim = mode == 0 ? cin : cout;
     HD_REQUIRE(rows_pad >= rows && k_pad >= kdim, "pack_conv_weight: padding smaller than the matrix");
     const int total = ksize * ksize * rows_pad * k_pad;
-    HD_CHECK_CUDA(::hd::launch_k(pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w_oihw, reinterpret_cast<__nv_bfloat16*>(out), cout, cin, ksize * ksize, rows_pad, k_pad, mode));
+    HD_CHECK_CUDA(::hd::launch_k(pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w_oihw,
+                                 reinterpret_cast<__nv_bfloat16*>(out), cout, cin, ksize * ksize, rows_pad, k_pad,
+                                 mode));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -122,7 +125,8 @@ extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, i
     HD_REQUIRE(c_pad >= C, "nchw_to_nhwc: c_pad < C");
     const size_t total = static_cast<size_t>(N) * H * W * c_pad;
     if (total == 0) return HD_OK;
-    HD_CHECK_CUDA(::hd::launch_k(nchw_to_nhwc_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, c_pad));
+    HD_CHECK_CUDA(::hd::launch_k(nchw_to_nhwc_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, x,
+                                 reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, c_pad));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -133,7 +137,8 @@ extern "C" int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, i
     HD_REQUIRE(c_stride >= C, "nhwc_to_nchw: c_stride < C");
     const size_t total = static_cast<size_t>(N) * C * H * W;
     if (total == 0) return HD_OK;
-    HD_CHECK_CUDA(::hd::launch_k(nhwc_to_nchw_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), y, N, C, H, W, c_stride));
+    HD_CHECK_CUDA(::hd::launch_k(nhwc_to_nchw_kernel, (unsigned)((total + 255) / 256), 256, 0, stream,
+                                 reinterpret_cast<const __nv_bfloat16*>(x), y, N, C, H, W, c_stride));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

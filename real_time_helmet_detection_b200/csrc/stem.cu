@@ -93,7 +93,8 @@ extern "C" int hd_stem_im2col(const float* x, void* patches, int N, int H, int W
     const int Ho = H / 2, Wo = W / 2;
     const long long tiles = static_cast<long long>(N) * ((Ho + kTOH - 1) / kTOH) * ((Wo + kTOW - 1) / kTOW);
     HD_REQUIRE(tiles < (1ll << 31), "stem_im2col: too many tiles");
-    HD_CHECK_CUDA(::hd::launch_k(stem_im2col_kernel, static_cast<unsigned>(tiles), 256, 0, stream, x, reinterpret_cast<__nv_bfloat16*>(patches), N, H, W));
+    HD_CHECK_CUDA(::hd::launch_k(stem_im2col_kernel, static_cast<unsigned>(tiles), 256, 0, stream, x,
+                                 reinterpret_cast<__nv_bfloat16*>(patches), N, H, W));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -102,7 +103,8 @@ extern "C" int hd_stem_pack_weight(const float* w, void* out, int cout, cudaStre
     using namespace hd;
     HD_REQUIRE(cout > 0 && cout <= 64, "stem_pack_weight: cout=%d", cout);
     const int total = cout * kStemKPad;
-    HD_CHECK_CUDA(::hd::launch_k(stem_pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w, reinterpret_cast<__nv_bfloat16*>(out), cout));
+    HD_CHECK_CUDA(::hd::launch_k(stem_pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w,
+                                 reinterpret_cast<__nv_bfloat16*>(out), cout));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

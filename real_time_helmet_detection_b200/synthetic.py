@@ -10,8 +10,9 @@ import numpy as np
 from .transform import box2hm
 
 
-def synthetic_targets(batch, imsize=512, num_cls=2, scale_factor=4, max_boxes=5):
-    outs = [[], [], [], []]
+def synthetic_boxes(batch, imsize=512, num_cls=2, max_boxes=5):
+    """The box lists behind `synthetic_targets`: per image (boxes [[x0,y0,x1,y1], ...], labels [...])."""
+    out = []
     for b in range(batch):
         rs = np.random.RandomState(b)
         nb = rs.randint(1, max_boxes + 1)
@@ -21,6 +22,13 @@ def synthetic_targets(batch, imsize=512, num_cls=2, scale_factor=4, max_boxes=5)
             bw, bh = rs.uniform(0.05, 0.3, 2) * imsize
             boxes.append([x0, y0, min(x0 + bw, imsize - 1), min(y0 + bh, imsize - 1)])
             labels.append(int(rs.randint(0, num_cls)))
+        out.append((boxes, labels))
+    return out
+
+
+def synthetic_targets(batch, imsize=512, num_cls=2, scale_factor=4, max_boxes=5):
+    outs = [[], [], [], []]
+    for boxes, labels in synthetic_boxes(batch, imsize, num_cls, max_boxes):
         for lst, arr in zip(outs, box2hm(boxes, labels, (imsize, imsize), scale_factor, num_cls)):
             lst.append(arr)
     return tuple(np.stack(o) for o in outs)

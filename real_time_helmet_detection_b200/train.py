@@ -65,12 +65,14 @@ class DevicePrefetcher:
         self._preload()
 
     def _preload(self):
-        try:
-            host = next(self.it)
-        except StopIteration:
-            self.next = None
-            return
+        # the iterator itself runs under the side stream too: a device-side collate (data.DeviceCollate) then issues its
+        # H2D copies and its normalise / GT-encode kernels there, off the compute stream
         with torch.cuda.stream(self.stream):
+            try:
+                host = next(self.it)
+            except StopIteration:
+                self.next = None
+                return
             self.next = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in host)
 
     def __iter__(self):

@@ -76,3 +76,49 @@ def test_flat_allreduce_two_gpus():
         assert err < 1e-5, err                              # synced == mean of the two ranks' local gradients
         assert drift < 0.5, drift                           # same shard, second run: only reduction-order noise
     assert torch.equal(res[0][4], res[1][4])                # both ranks hold identical averaged gradients
+
+
+def _worker_torch_ddp(rank, world, port, q):
+    """The reference's own wrapper (train.py:174-175): torch DistributedDataParallel around our module."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from torch.nn.parallel import DistributedDataParallel
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.loss import LossCalculator
+    from real_time_helmet_detection_b200.synthetic import synthetic_targets
+    torch.manual_seed(100 + rank)
+    net = StackedHourglass(1, 128, 6).to(dev).train()
+    ddp = DistributedDataParallel(net, device_ids=[rank])          # broadcasts rank 0's parameters and buffers
+    crit = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0)
+    g = torch.Generator().manual_seed(5)
+    x_all = torch.randn(4, 3, 128, 128, generator=g)
+    gts_all = [torch.from_numpy(a).to(dev) for a in synthetic_targets(4, imsize=128)]
+    shard = slice(2 * rank, 2 * rank + 2)
+    out = ddp(x_all[shard].to(dev))
+    loss = crit.forward_logits(out[:, 0], *[t[shard] for t in gts_all])
+    loss.backward()
+    flat = torch.cat([p.grad.flatten() for p in net.parameters()])
+    w0 = torch.cat([p.detach().flatten() for p in net.parameters()])[:1000].cpu()
+    q.put((rank, bool(torch.isfinite(flat).all()), float(flat.norm()), flat[:1000].cpu(), w0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_torch_ddp_wrapper_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker_torch_ddp, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res) and res[0][2] > 0
+    assert torch.equal(res[0][4], res[1][4])                 # parameters were broadcast from rank 0
+    assert torch.equal(res[0][3], res[1][3])                 # DDP's reducer averaged the gradients of our backward node

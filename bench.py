@@ -226,13 +226,36 @@ def decode_latency(torch, dev, S=1, runs=300):
     e1.record()
     torch.cuda.synchronize()
     dev_us = e0.elapsed_time(e1) * 1e3 / runs
+    # the same two launches replayed from a CUDA graph ("also report with CUDA-graph replay")
+    graph_us = None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            _decode_call(head, off_v, wh_v, strides, B, S_, C, H, W, 100, 4, 0.2, 0.2, False, True, True, bufs=bufs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            _decode_call(head, off_v, wh_v, strides, B, S_, C, H, W, 100, 4, 0.2, 0.2, False, True, True, bufs=bufs)
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(runs):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_us = e0.elapsed_time(e1) * 1e3 / runs
+    except Exception as exc:      # keep the benchmark line alive if capture is not possible on some driver
+        graph_us = f"unavailable: {type(exc).__name__}"
     wall = []
     for _ in range(runs):
         t0 = time.perf_counter()
         b, c, s = pred.decode(head)       # includes the count D2H read (the one sync the API's output shapes need)
         wall.append(time.perf_counter() - t0)
     return {"workload": f"decode+NMS 512x512 batch 1, {S} stack, topk 100, conf 0.2, nms 0.2", "device_us": dev_us,
-            "api_wall_us": statistics.median(wall) * 1e6, "boxes": int(b[0].shape[0]),
+            "graph_replay_us": graph_us, "api_wall_us": statistics.median(wall) * 1e6, "boxes": int(b[0].shape[0]),
             "algorithmic_bytes": 6 * H * W * 4 * S, "reference_cpu_us": "1450 (BASELINE.md, 8 vCPU Xeon, this container)"}
 
 

@@ -114,6 +114,18 @@ int hd_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W
  * then hd_conv2d_igemm(cin=192, ksize=1) with weights from hd_stem_pack_weight ([1][64][192]). */
 int hd_stem_im2col(const float* x, void* patches, int N, int H, int W, hd_stream_t stream);
 int hd_stem_pack_weight(const float* w, void* out, int cout, hd_stream_t stream);
+/* Space-to-depth formulation of the same stem (csrc/stem.cu): unfolded [N][H/2][W/2][64] bf16 with
+ * unfolded[.., dx*12 + (c*2+sy)*2 + sx] = img[c][2Y+sy][2(X+dx-2)+sx] (48 of 64 channels used, zero outside the image):
+ * the stem is then four vertical taps over it - hd_conv2d_igemm_vtaps with packed weights [4][64][64] (pack mode 3 of the
+ * executor) - and its weight gradient hd_conv2d_wgrad(.., cin 64, cin_real 48, cout 64, ksize 1, stem_perm 2). */
+int hd_stem_unfold(const float* x_nchw, void* unfolded, int N, int H, int W, hd_stream_t stream);
+/* Convolution with a COLUMN of `vtaps` vertical taps (input rows y - pad_top .. y - pad_top + vtaps - 1, same column):
+ * w_packed [vtaps][block_n][cin] bf16. Train mode: stat_sum / stat_sqsum (+ optional fused BN finalize `bn`); eval mode:
+ * optional per-channel scale / shift (+ ReLU) epilogue. Generic kernel only. */
+int hd_conv2d_igemm_vtaps(const void* x, const void* w_packed, void* out, const float* bias, float* stat_sum,
+                          float* stat_sqsum, int N, int H, int W, int cin, int cout, int block_n, int vtaps, int pad_top,
+                          int out_cs, const hd_bn_fuse* bn, const float* scale, const float* shift, int relu,
+                          hd_stream_t stream);
 
 /* Backward of the 1x1 prediction head (hourglass.py:189-195). dw/dbias are accumulated into. */
 int hd_head_backward(const float* dlogits, long long batch_stride, const void* extra, int extra_cs, const void* feat,

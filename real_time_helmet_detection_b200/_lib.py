@@ -35,11 +35,14 @@ _SIGNATURES = {
     "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_wgrad_ksplit": (I, [I, I, I, I]),
     "hd_conv2d_wgrad_workspace_bytes": (c_size_t, [I, I, I, I, I]),
+    "hd_pack_all_weights": (I, [P, I, LL, P]),
     "hd_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, P]),
     "hd_nchw_f32_to_nhwc_bf16": (I, [P, P, I, I, I, I, I, P]),
     "hd_nhwc_bf16_to_nchw_f32": (I, [P, P, I, I, I, I, I, P]),
     "hd_stem_im2col": (I, [P, P, I, I, I, P]),
     "hd_stem_pack_weight": (I, [P, P, I, P]),
+    "hd_stem_unfold": (I, [P, P, I, I, I, P]),
+    "hd_conv2d_igemm_vtaps": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, I, P]),
     "hd_head_backward": (I, [P, LL, P, I, P, P, P, P, P, I, I, I, I, P]),
     "hd_bn_finalize": (I, [P, P, F, P, P, P, P, P, F, F, I, P, P, P, P, I, P]),
     "hd_bn_act": (I, [P, P, P, P, LL, I, I, P]),

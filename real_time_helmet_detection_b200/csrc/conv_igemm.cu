@@ -33,6 +33,8 @@ struct ConvParams {
     int N, H, W;          // output == input spatial size (stride 1, "same" padding)
     int cin_chunks;       // Cin / 64
     int kh, kw, pad;      // taps
+    int pad_y, pad_x;     // generic kernel: tap offsets dy = tap / kw - pad_y, dx = tap % kw - pad_x (== pad for k x k convs;
+                          // the space-to-depth stem is a 4 x 1 column of taps with pad_y = 2, pad_x = 0)
     int cout;             // real output channels (<= BLOCK_N)
     int tw_log2, th_log2, tn_log2;
     int tiles_x, tiles_y, tiles_n, num_tiles;
@@ -272,7 +274,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const int tn = tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << p.tn_log2;
                 for (int tap = 0; tap < p.kh * p.kw; ++tap) {
-                    const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                    const int dy = tap / p.kw - p.pad_y, dx = tap % p.kw - p.pad_x;
                     for (int ck = 0; ck < p.cin_chunks; ++ck) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * kStageBytes;
@@ -691,7 +693,7 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
                          const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int vtaps = 0, int pad_top = 0);
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
@@ -721,11 +723,21 @@ extern "C" int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void*
                          out_cs, 0, 0, 1, nullptr, scale, shift, relu, stream);
 }
 
+extern "C" int hd_conv2d_igemm_vtaps(const void* x, const void* w_packed, void* out, const float* bias, float* stat_sum,
+                                     float* stat_sqsum, int N, int H, int W, int cin, int cout, int block_n, int vtaps,
+                                     int pad_top, int out_cs, const hd_bn_fuse* bn, const float* scale,
+                                     const float* shift, int relu, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(vtaps >= 1, "conv_igemm_vtaps: vtaps=%d", vtaps);
+    return conv_dispatch(x, w_packed, out, nullptr, bias, nullptr, stat_sum, stat_sqsum, N, H, W, cin, cout, block_n, 1, 0,
+                         out_cs, 0, 0, 1, bn, scale, shift, relu, stream, vtaps, pad_top);
+}
+
 static int conv_dispatch(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
                          const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int vtaps, int pad_top) {
     using namespace hd;
     HD_REQUIRE(bn == nullptr || (stat_sum != nullptr && bn->out && bn->counter && bn->gamma && bn->beta),
                "conv_igemm: fused BN finalize needs statistics, gamma/beta, an output block and a ticket counter");
@@ -744,6 +756,11 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
     p.cin_chunks = cin / 64;
     p.kh = p.kw = ksize;
     p.pad = (ksize - 1) / 2;
+    p.pad_y = p.pad_x = p.pad;
+    if (vtaps > 0) {        // a column of `vtaps` vertical taps (rows y - pad_top .. y - pad_top + vtaps - 1), generic kernel only
+        HD_REQUIRE(ksize == 1 && vtaps <= 8 && pad_top >= 0 && pad_top < vtaps, "conv_igemm: vtaps=%d pad_top=%d", vtaps, pad_top);
+        p.kh = vtaps; p.kw = 1; p.pad_y = pad_top; p.pad_x = 0;
+    }
     p.cout = cout;
     int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
@@ -766,7 +783,7 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
     // halo kernel: 3x3 (or 1x1: same kernel, one tap, no halo rows), 128 output channels, map >= 16x16 and enough 16x16
     // tiles to fill the machine
     bool halo = false;
-    if ((ksize == 3 || ksize == 1) && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 &&
+    if ((ksize == 3 || ksize == 1) && vtaps == 0 && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 &&
         g_conv_variant != 1) {
         const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
         halo = g_conv_variant == 2 || ht >= sm_count();
@@ -785,7 +802,7 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
         if (rc) return rc;
     }
     {
-        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)block_n, (uint64_t)(ksize * ksize)};
+        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)block_n, (uint64_t)(p.kh * p.kw)};
         uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)block_n * cin * 2};
         uint32_t box[3] = {64, (uint32_t)block_n, 1};
         int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);

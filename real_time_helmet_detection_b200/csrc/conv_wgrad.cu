@@ -24,7 +24,8 @@ constexpr int kWgABytes = 2 * 128 * 128;  // dY tile: 128 pixels x 128 cout (two
 
 struct WgradParams {
     int N, H, W;
-    int kw, pad;               // taps per row, padding
+    int kw, pad, pad_x;        // taps per row; tap offsets dy = tap / kw - pad, dx = tap % kw - pad_x (pad_x == pad unless the
+                               // taps are a vertical column: space-to-depth stem, kw = 1, pad = 2, pad_x = 0)
     int taps_per_group;        // 3 (3x3) or 1 (1x1)
     int groups;                // 3 or 1
     int ksplit;
@@ -116,7 +117,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 } else {
                     for (int t = 0; t < p.taps_per_group; ++t) {
                         const int tap = group * p.taps_per_group + t;
-                        const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                        const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad_x;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
 #pragma unroll
@@ -238,9 +239,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     const float* src = ws + (static_cast<size_t>(tap) * rows_pad + co) * cin_pad + ci;
     for (int k = 0; k < ksplit; ++k) s += src[k * stride];
     float* g = grad + (static_cast<size_t>(co) * cin + ci) * taps + tap;
-    if (stem_perm) {
+    if (stem_perm == 1) {
         const int c = ci % 3, kk = ci / 3;   // kk = ky*7 + kx
         g = grad + (static_cast<size_t>(co) * 3 + c) * 49 + kk;
+    } else if (stem_perm == 2) {             // space-to-depth stem (stem.cu): tap = dy, ci = dx*12 + (c*2+sy)*2 + sx
+        const int dx = ci / 12, q = ci % 12, c = q >> 2, sy = (q >> 1) & 1, sx = q & 1;
+        const int ky = 2 * tap + sy - 1, kx = 2 * dx + sx - 1;
+        if (ky < 0 || kx < 0) return;        // the zero-weight taps of the 8x8 -> 7x7 embedding
+        g = grad + (static_cast<size_t>(co) * 3 + c) * 49 + ky * 7 + kx;
     }
     *g = accumulate ? (*g + s) : s;
 }
@@ -279,7 +285,9 @@ extern "C" int hd_conv2d_wgrad_ksplit(int N, int H, int W, int ksize) {
 
 extern "C" size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int ksize) {
     int ks = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
-    return static_cast<size_t>(ks) * ksize * ksize * 128 * cin * sizeof(float);
+    // at least 4 taps: the space-to-depth stem (stem_perm 2) runs as ksize 1 with four vertical taps
+    const int taps = (ksize == 1 && cin == 64) ? 4 : ksize * ksize;
+    return static_cast<size_t>(ks) * taps * 128 * cin * sizeof(float);
 }
 
 // See include/hd_b200.h.
@@ -290,16 +298,21 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     // cout == 64: the second 64-channel atom of the dY tile is fetched out of bounds and zero-filled by TMA.
     HD_REQUIRE(cout == 128 || cout == 64, "conv_wgrad: cout=%d (tensor-core path needs 64 or 128)", cout);
     HD_REQUIRE(cin == 64 || cin == 128 || (cin == 192 && ksize == 1), "conv_wgrad: cin=%d unsupported", cin);
-    HD_REQUIRE(!stem_perm || (cin == 192 && cin_real == 147 && ksize == 1), "conv_wgrad: stem_perm needs K=147/192");
+    HD_REQUIRE(stem_perm != 1 || (cin == 192 && cin_real == 147 && ksize == 1), "conv_wgrad: stem_perm 1 needs K=147/192");
+    HD_REQUIRE(stem_perm != 2 || (cin == 64 && cin_real == 48 && ksize == 1 && cout == 64),
+               "conv_wgrad: stem_perm 2 (space-to-depth stem) needs cin 64 (48 real), cout 64");
     HD_REQUIRE(cin_real >= 1 && cin_real <= cin, "conv_wgrad: cin_real=%d", cin_real);
     HD_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize=%d unsupported", ksize);
     HD_REQUIRE(N > 0 && H > 0 && W > 0, "conv_wgrad: empty tensor");
     WgradParams p{};
     p.N = N; p.H = H; p.W = W;
-    p.kw = ksize; p.pad = (ksize - 1) / 2;
+    p.kw = ksize; p.pad = (ksize - 1) / 2; p.pad_x = p.pad;
     p.taps = ksize * ksize;
     p.groups = ksize == 3 ? 3 : 1;
     p.taps_per_group = ksize == 3 ? 3 : 1;
+    if (stem_perm == 2) {       // a column of four vertical taps (rows y-2 .. y+1) kept resident by ONE tap group
+        p.kw = 1; p.pad = 2; p.pad_x = 0; p.taps = 4; p.groups = 1; p.taps_per_group = 4;
+    }
     int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
     int tn = 128 / (tw * th);

@@ -156,6 +156,13 @@ static void phase_report(hd_net* n) {
     n->phases.clear();
 }
 
+// The stem runs in its space-to-depth formulation (csrc/stem.cu: x-unfolded 64-channel tensor + four vertical taps);
+// HD_STEM_IM2COL=1 selects the first version (147 -> 192 im2col patch matrix, 3x the traffic).
+static bool stem_s2d() {
+    static const bool im2col = getenv("HD_STEM_IM2COL") != nullptr;
+    return !im2col;
+}
+
 static const hd_unit_ptrs kNullUnit{};
 static inline const hd_unit_ptrs& UP(const hd_net* n, int ui) { return n->up ? n->up[ui] : kNullUnit; }
 
@@ -249,7 +256,7 @@ static void plan_persistent(hd_net* n) {
         u.bnp = reinterpret_cast<float*>(a.alloc(4 * u.cout * sizeof(float)));
         const int taps = u.kind == 1 ? 1 : u.k * u.k;
         if (u.kind == 1) {
-            u.wp = reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(64) * 192 * 2));
+            u.wp = reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(64) * 256 * 2));    // [64][192] or [4 taps][64][64]
             u.wpd = nullptr;
         } else {
             u.wp = reinterpret_cast<bf16*>(a.alloc(static_cast<size_t>(taps) * block_n_for(u.cout) * pad64(u.cin) * 2));
@@ -309,8 +316,13 @@ static void pack_weights(hd_net* n, bool need_dgrad) {
         PackJobHost j{};
         j.w = p.w; j.cout = u.cout; j.cin = u.cin;
         if (u.kind == 1) {
-            j.out = u.wp; j.taps = 1; j.rows_pad = 64; j.k_pad = 192; j.mode = 2;
-            j.start = total; total += 64ll * 192; jobs.push_back(j);
+            if (stem_s2d()) {
+                j.out = u.wp; j.taps = 4; j.rows_pad = 64; j.k_pad = 64; j.mode = 3;
+                j.start = total; total += 4ll * 64 * 64; jobs.push_back(j);
+            } else {
+                j.out = u.wp; j.taps = 1; j.rows_pad = 64; j.k_pad = 192; j.mode = 2;
+                j.start = total; total += 64ll * 192; jobs.push_back(j);
+            }
             continue;
         }
         j.taps = u.k * u.k;
@@ -388,6 +400,20 @@ static void conv_unit(hd_net* n, int ui, const bf16* x, bf16* y, int B, int H, i
     const int k = u.kind == 1 ? 1 : u.k;
     const bool stats = u.bn && training;
     u.npix = static_cast<long long>(B) * H * W;
+    if (u.kind == 1 && stem_s2d()) {
+        // x = the x-unfolded space-to-depth tensor (64 channels): four vertical taps, rows y-2 .. y+1
+        hd_bn_fuse bn{};
+        bn.gamma = p.gamma; bn.beta = p.beta; bn.running_mean = p.running_mean; bn.running_var = p.running_var;
+        bn.num_batches_tracked = p.num_batches_tracked; bn.momentum = 0.1f; bn.eps = 1e-5f;
+        bn.out = u.bnp; bn.counter = n->tickets + ui;
+        if (stats)
+            RUN(hd_conv2d_igemm_vtaps(x, u.wp, y, p.b, u.stats, u.stats + u.cout, B, H, W, 64, u.cout, 64, 4, 2, u.cout, &bn,
+                                      nullptr, nullptr, 0, n->stream));
+        else
+            RUN(hd_conv2d_igemm_vtaps(x, u.wp, y, p.b, nullptr, nullptr, B, H, W, 64, u.cout, 64, 4, 2, u.cout, nullptr,
+                                      u.bnp, u.bnp + u.cout, eval_relu, n->stream));
+        return;
+    }
     if (stats) {
         // train mode: the conv's last CTA finalizes the BN (scale/shift/mean/rstd + running statistics) itself
         hd_bn_fuse bn{};
@@ -498,10 +524,11 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     phase_mark(n, "fwd:start");
     // ---- PreLayer (hourglass.py:159-173)
     Unit& u0 = n->units[0];
-    n->patches = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 192)));
+    n->patches = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, stem_s2d() ? 64 : 192)));
     n->Y0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
     n->Z0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
-    RUN(hd_stem_im2col(x, n->patches, B, H, W, n->stream));
+    if (stem_s2d()) RUN(hd_stem_unfold(x, n->patches, B, H, W, n->stream));
+    else RUN(hd_stem_im2col(x, n->patches, B, H, W, n->stream));
     if (training) {
         conv_unit(n, 0, n->patches, n->Y0, B, H2, W2, nullptr, training);
         RUN(hd_bn_act(n->Y0, u0.bnp, u0.bnp + 64, n->Z0, static_cast<long long>(B) * H2 * W2, 64, 1, n->stream));
@@ -571,7 +598,9 @@ static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, 
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
     wait_on(n, n->side, ready);
-    if (u.kind == 1)
+    if (u.kind == 1 && stem_s2d())
+        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 64, 48, 64, 1, 0, 2, n->side));
+    else if (u.kind == 1)
         RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->side));
     else
         RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->side));
@@ -774,6 +803,7 @@ static size_t max_wgrad_ws(int B, int H, int W) {
     size_t m = 0;
     const int H2 = H / 2, W2 = W / 2;
     size_t v = hd_conv2d_wgrad_workspace_bytes(B, H2, W2, 192, 1); if (v > m) m = v;
+    v = hd_conv2d_wgrad_workspace_bytes(B, H2, W2, 64, 1); if (v > m) m = v;      // space-to-depth stem: 4 taps x 64
     v = hd_conv2d_wgrad_workspace_bytes(B, H2, W2, 128, 3); if (v > m) m = v;
     for (int h = H / 4, w = W / 4; h >= 1 && w >= 1; h /= 2, w /= 2) {
         v = hd_conv2d_wgrad_workspace_bytes(B, h, w, 128, 3);

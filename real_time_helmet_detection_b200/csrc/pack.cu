@@ -62,7 +62,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 struct PackJob {
     const float* w;
     __nv_bfloat16* out;
-    int cout, cin, taps, rows_pad, k_pad, mode;   // mode 0 forward, 1 dgrad, 2 stem (K = (ky*7+kx)*3+c, padded)
+    int cout, cin, taps, rows_pad, k_pad, mode;   // mode 0 forward, 1 dgrad, 2 stem im2col (K = (ky*7+kx)*3+c, padded), 3 stem space-to-depth
     long long start;
 };
 
@@ -85,8 +85,14 @@ __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, lon
         if (r < j.cout && k < j.cin) v = j.w[(static_cast<size_t>(r) * j.cin + k) * j.taps + tap];
     } else if (j.mode == 1) {
         if (r < j.cin && k < j.cout) v = j.w[(static_cast<size_t>(k) * j.cin + r) * j.taps + (j.taps - 1 - tap)];
-    } else {
+    } else if (j.mode == 2) {
         if (r < j.cout && k < 147) v = j.w[(static_cast<size_t>(r) * 3 + (k % 3)) * 49 + (k / 3)];
+    } else {        // mode 3: space-to-depth stem (stem.cu): tap = dy, k = dx*12 + (c*2+sy)*2 + sx -> w[r][c][2dy+sy-1][2dx+sx-1]
+        if (r < j.cout && k < 48) {
+            const int dx = k / 12, q = k % 12, c = q >> 2, sy = (q >> 1) & 1, sx = q & 1;
+            const int ky = 2 * tap + sy - 1, kx = 2 * dx + sx - 1;
+            if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = j.w[(static_cast<size_t>(r) * 3 + c) * 49 + ky * 7 + kx];
+        }
     }
     j.out[e] = __float2bfloat16(v);
 }

@@ -71,6 +71,61 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Space-to-depth formulation of the same stem (the default): a 7x7 stride-2 pad-3 convolution over (3, H, W) is a
+// 4x4 stride-1 convolution over the space-to-depth image S[c, sy, sx](Y, X) = img[c, 2Y+sy, 2X+sx] (12 channels):
+//     out[oy, ox] = sum_{dy,dx in 0..3} sum_{c,sy,sx} w[c, 2dy+sy-1, 2dx+sx-1] * S[c,sy,sx](oy+dy-2, ox+dx-2)
+// (taps with ky or kx = -1 have weight 0). Only the HORIZONTAL taps are unfolded into channels,
+//     U[n, Y, X, dx*12 + (c*2+sy)*2 + sx] = S[c,sy,sx](Y, X+dx-2),   48 of 64 channels used,
+// so U is 128 B per pixel = 268 MB at B=32 instead of the 805 MB im2col patch matrix, and the four VERTICAL taps are
+// row-shifted TMA boxes of the implicit-GEMM kernel (hd_conv2d_igemm_vtaps: K = 4 x 64) and of the wgrad kernel.
+constexpr int kUTOH = 4, kUTOW = 64;
+constexpr int kUPH = 2 * kUTOH, kUPW = 2 * kUTOW + 6;
+
+__global__ void __launch_bounds__(256) stem_unfold_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int N, int H, int W) {
+    pdl_prologue();
+    __shared__ float patch[3][kUPH][kUPW + 1];
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int tiles_x = (Wo + kUTOW - 1) / kUTOW, tiles_y = (Ho + kUTOH - 1) / kUTOH;
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+    const int oy0 = ty * kUTOH, ox0 = tx * kUTOW;
+    const int iy0 = 2 * oy0, ix0 = 2 * (ox0 - 2);
+    for (int i = threadIdx.x; i < 3 * kUPH * kUPW; i += blockDim.x) {
+        const int px = i % kUPW, py = (i / kUPW) % kUPH, c = i / (kUPW * kUPH);
+        const int iy = iy0 + py, ix = ix0 + px;
+        float v = 0.f;
+        if (iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<size_t>(n) * 3 + c) * H + iy) * W + ix);
+        patch[c][py][px] = v;
+    }
+    __syncthreads();
+    const float* pbase = &patch[0][0][0];
+    // thread -> one fixed 8-k vector of 32 pixels per pass; vectors 6 and 7 (k >= 48) are the zero padding
+    const int kv = threadIdx.x & 7, slot = threadIdx.x >> 3;
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = kv * 8 + j;
+        const int dx = k / 12, r = k % 12, c = r >> 2, sy = (r >> 1) & 1, sx = r & 1;
+        off[j] = k < 48 ? (c * kUPH + sy) * (kUPW + 1) + 2 * dx + sx : -1;
+    }
+    for (int lp = slot; lp < kUTOH * kUTOW; lp += 32) {
+        const int lx = lp % kUTOW, ly = lp / kUTOW;
+        const int oy = oy0 + ly, ox = ox0 + lx;
+        if (oy >= Ho || ox >= Wo) continue;
+        const int pofs = (2 * ly) * (kUPW + 1) + 2 * lx;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? pbase[off[j] + pofs] : 0.f;
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * 64 + kv * 8) = u;
+    }
+}
+
 // w: [64][3][7][7] fp32 -> out: [1][64][192] bf16 in the im2col K order
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout) {
     pdl_prologue();
@@ -105,6 +160,18 @@ extern "C" int hd_stem_pack_weight(const float* w, void* out, int cout, cudaStre
     const int total = cout * kStemKPad;
     HD_CHECK_CUDA(::hd::launch_k(stem_pack_weight_kernel, (total + 255) / 256, 256, 0, stream, w,
                                  reinterpret_cast<__nv_bfloat16*>(out), cout));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_stem_unfold(const float* x, void* unfolded, int N, int H, int W, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "stem_unfold: shape (%d,3,%d,%d)", N, H, W);
+    const int Ho = H / 2, Wo = W / 2;
+    const long long tiles = static_cast<long long>(N) * ((Ho + kUTOH - 1) / kUTOH) * ((Wo + kUTOW - 1) / kUTOW);
+    HD_REQUIRE(tiles < (1ll << 31), "stem_unfold: too many tiles");
+    HD_CHECK_CUDA(::hd::launch_k(stem_unfold_kernel, static_cast<unsigned>(tiles), 256, 0, stream, x,
+                                 reinterpret_cast<__nv_bfloat16*>(unfolded), N, H, W));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

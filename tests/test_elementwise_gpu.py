@@ -232,6 +232,60 @@ def test_stem_forward_wgrad(cuda_device):
     assert ((gw - gref).norm() / gref.norm()).item() <= 1e-4
 
 
+def test_stem_space_to_depth_path(cuda_device):
+    """The default stem: x-unfolded space-to-depth tensor (hd_stem_unfold) + four vertical taps (hd_conv2d_igemm_vtaps,
+    weights packed by pack mode 3) + wgrad with the space-to-depth gradient mapping (stem_perm 2) == F.conv2d(7x7, s2, p3)."""
+    import ctypes
+    from real_time_helmet_detection_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(19)
+    d = cuda_device
+    N, H, W = 2, 64, 96
+    x = bf(torch.randn(N, 3, H, W, generator=g))
+    w = bf(torch.randn(64, 3, 7, 7, generator=g) * 0.1)
+    b = torch.randn(64, generator=g)
+    ref = F.conv2d(x, w, b, stride=2, padding=3)
+    Ho, Wo = H // 2, W // 2
+    xd = x.to(d).contiguous()
+    U = torch.full((N, Ho, Wo, 64), 7.0, dtype=torch.bfloat16, device=d)
+    _lib.check(L.hd_stem_unfold(_lib.ptr(xd), _lib.ptr(U), N, H, W, _lib.stream()))
+    # U[n, Y, X, dx*12 + (c*2+sy)*2 + sx] = x[n, c, 2Y+sy, 2(X+dx-2)+sx], zero outside / for k >= 48
+    xp = F.pad(x, (4, 4, 0, 0))
+    want = torch.zeros(N, Ho, Wo, 64)
+    for dx in range(4):
+        for c in range(3):
+            for sy in range(2):
+                for sx in range(2):
+                    cols = torch.arange(Wo) * 2 + 2 * dx + sx              # 2(X+dx-2)+sx+4 in the padded image
+                    want[..., dx * 12 + (c * 2 + sy) * 2 + sx] = xp[:, c, sy::2][:, :, cols]
+    assert torch.equal(U.float().cpu(), want)
+
+    class Job(ctypes.Structure):
+        _fields_ = [("w", ctypes.c_void_p), ("out", ctypes.c_void_p), ("cout", ctypes.c_int), ("cin", ctypes.c_int),
+                    ("taps", ctypes.c_int), ("rows_pad", ctypes.c_int), ("k_pad", ctypes.c_int), ("mode", ctypes.c_int),
+                    ("start", ctypes.c_longlong)]
+    wd = w.to(d).contiguous()
+    wp = torch.empty(4, 64, 64, dtype=torch.bfloat16, device=d)
+    job = Job(wd.data_ptr(), wp.data_ptr(), 64, 3, 4, 64, 64, 3, 0)
+    jd = torch.frombuffer(bytearray(bytes(job)), dtype=torch.uint8).to(d)
+    _lib.check(L.hd_pack_all_weights(_lib.ptr(jd), 1, 4 * 64 * 64, _lib.stream()))
+    y = torch.empty(N, Ho, Wo, 64, dtype=torch.bfloat16, device=d)
+    stats = torch.zeros(2, 64, device=d)
+    bd = b.to(d)
+    _lib.check(L.hd_conv2d_igemm_vtaps(_lib.ptr(U), _lib.ptr(wp), _lib.ptr(y), _lib.ptr(bd), _lib.ptr(stats[0]),
+                                       _lib.ptr(stats[1]), N, Ho, Wo, 64, 64, 64, 4, 2, 64, None, None, None, 0, _lib.stream()))
+    close_bf16(nchw(y), ref, extra=1e-3 * ref.abs().max().item())
+    assert torch.allclose(stats[0].cpu(), ref.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+    dy = bf(torch.randn(N, 64, Ho, Wo, generator=g))
+    gref = torch.nn.grad.conv2d_weight(x, (64, 3, 7, 7), dy, stride=2, padding=3)
+    gw = torch.full((64, 3, 7, 7), 9.0, device=d)
+    dyd = nhwc(dy, d)
+    ws = torch.empty(L.hd_conv2d_wgrad_workspace_bytes(N, Ho, Wo, 64, 1), dtype=torch.uint8, device=d)
+    _lib.check(L.hd_conv2d_wgrad(_lib.ptr(U), _lib.ptr(dyd), _lib.ptr(gw), _lib.ptr(ws), N, Ho, Wo, 64, 48, 64, 1, 0, 2,
+                                 _lib.stream()))
+    assert ((gw.cpu() - gref).norm() / gref.norm()).item() <= 1e-4
+
+
 def test_head_backward(cuda_device):
     from real_time_helmet_detection_b200 import ops
     g = torch.Generator().manual_seed(4)

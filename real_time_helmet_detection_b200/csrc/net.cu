@@ -507,6 +507,7 @@ static bf16* hourglass_fwd(hd_net* n, int hi, bf16* x, int B, int H, int W, int 
 static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H, int W, int training) {
     const int C = n->in_ch;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+    cudaEvent_t packed = nullptr;
     if (!n->dry) {
         if (n->rc == 0 && cudaMemsetAsync(n->units[0].stats, 0, n->persist_bytes, n->stream) != cudaSuccess)
             n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN statistics failed");
@@ -515,8 +516,14 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
             n->rc = fail(HD_ERR_CUDA, "net_forward: memset of the BN-backward scratch failed");
         const bool reuse = !training && n->static_weights && n->eval_packed && n->eval_packed_ws == n->persist.base;
         if (!reuse) {
+            // weight packing (+ BN folding) on the second lane, beside the stem's unfold kernel, which needs no weights
+            cudaEvent_t start = mark_ready(n);
+            swap_lane(n);
+            wait_on(n, n->stream, start);
             pack_weights(n, training != 0);
             if (!training) fold_bn(n);
+            packed = mark_ready(n);
+            swap_lane(n);
         }
         n->eval_packed = !training;
         n->eval_packed_ws = n->persist.base;
@@ -529,6 +536,7 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     n->Z0 = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H2, W2, 64)));
     if (stem_s2d()) RUN(hd_stem_unfold(x, n->patches, B, H, W, n->stream));
     else RUN(hd_stem_im2col(x, n->patches, B, H, W, n->stream));
+    wait_on(n, n->stream, packed);      // the first convolution needs the packed weights
     if (training) {
         conv_unit(n, 0, n->patches, n->Y0, B, H2, W2, nullptr, training);
         RUN(hd_bn_act(n->Y0, u0.bnp, u0.bnp + 64, n->Z0, static_cast<long long>(B) * H2 * W2, 64, 1, n->stream));

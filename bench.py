@@ -94,8 +94,46 @@ def synthetic_batch(torch, B, size, seed):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+class CpuArm:
+    """The reference's train-loop body (train.py:99-134, with the out-of-place squeeze) on the host CPU, fp32.
+    kind "reference": the UNMODIFIED modules staged under baseline/_ref/ (hourglass.StackedHourglass, loss.LossCalculator,
+    optim.get_optimizer); kind "port": the oracle restatement (oracle/), used only when the reference is not staged."""
+
+    def __init__(self, torch, S):
+        from baseline import refload
+        self.torch, self.S = torch, S
+        self.kind = "reference" if refload.available() else "port"
+        if self.kind == "reference":
+            mods = refload.load_reference(("hourglass", "loss", "optim"))
+            torch.manual_seed(777)
+            self.net = mods["hourglass"].StackedHourglass(num_stack=S, in_ch=128, out_ch=6).train()
+            self.crit = mods["loss"].LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0)
+            self.opt, _ = mods["optim"].get_optimizer(self.net, 5e-4, None, 0.1)
+        else:
+            self.sd = cpu_model(torch, S)
+            self.opt = torch.optim.Adam([v for v in self.sd.values() if v.requires_grad], lr=5e-4)
+
+    def step(self, x, gts, adam=False):
+        torch = self.torch
+        if self.kind == "port":
+            loss = cpu_reference_step(torch, self.sd, x, gts, self.S)
+        else:
+            outputs = self.net(x)
+            total = 0
+            for output in outputs.split(1, dim=1):
+                output = output.squeeze(1)
+                phm, poff, psz = output.split([2, 2, 2], dim=1)
+                total = total + self.crit(torch.sigmoid(phm), poff, psz, *gts)
+            total.backward()
+            loss = float(total.detach())
+        if adam:
+            self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        return loss
+
+
 def cpu_reference_step(torch, sd, x, gts, S):
-    """The reference's train-loop body (train.py:99-134) on the oracle port: forward, per-stack loss, backward."""
+    """Oracle-port flavour of the same loop body (only when baseline/_ref is absent)."""
     from oracle import hourglass_ref, loss_ref
     for v in sd.values():
         if v.requires_grad:
@@ -126,24 +164,64 @@ def usable_cores():
     return max(1, n)
 
 
-def time_cpu(torch, S, size, batch, steps, warmup):
+def cpu_name():
+    try:
+        return [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        return ""
+
+
+def time_cpu(torch, S, size, batch, steps, warmup, adam=False, arm=None):
     # a batch-2 fp32 train step has parallel slack for a few dozen threads at most: beyond that PyTorch's intra-op
     # pool only adds contention (measured 50x slower with 128 threads on the pool's host), so threads are capped at 32
     cores = min(usable_cores(), 32)
     torch.set_num_threads(cores)
-    sd = cpu_model(torch, S)
+    arm = arm or CpuArm(torch, S)
     x, gts = synthetic_batch(torch, batch, size, 0)
     for i in range(warmup):
         t = time.perf_counter()
-        cpu_reference_step(torch, sd, x, gts, S)
+        arm.step(x, gts, adam)
         if time.perf_counter() - t > 20.0:        # very slow host: keep the run bounded
             steps = 1
             break
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(torch, sd, x, gts, S)
+        arm.step(x, gts, adam)
     dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt, cores
+    return batch / dt, dt, cores, arm.kind
+
+
+def cpu_decode_us(torch, S=1, runs=200):
+    """Config 5 on the host: the reference's `Prediction` minus the network (evaluate.py:126-182: per-stack split ->
+    sigmoid -> hm2box -> cat -> torchvision NMS) on the synthetic blob head, median wall time over `runs` calls.
+    kind "reference": the unmodified evaluate.Prediction / transform.hm2box from baseline/_ref; "port": oracle/decode_ref."""
+    from baseline import refload
+    from real_time_helmet_detection_b200.synthetic import synthetic_head
+    head = synthetic_head(S=S)
+    torch.set_num_threads(min(usable_cores(), 32))
+    if refload.available():
+        ev = refload.load_reference(("evaluate",))["evaluate"]
+        t = torch.from_numpy(head)
+
+        class Fixed(torch.nn.Module):
+            def forward(self, x):
+                return t.clone()
+
+        pred = ev.Prediction(Fixed(), 100, 4, 0.2, "nms", 0.2).eval()
+        fn, kind = (lambda: pred(None)), "reference"
+    else:
+        from oracle import decode_ref
+        fn, kind = (lambda: decode_ref.predict(head)), "port"
+    wall = []
+    with torch.no_grad():
+        for _ in range(10):
+            out = fn()
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            out = fn()
+            wall.append(time.perf_counter() - t0)
+    return {"us": statistics.median(wall) * 1e6, "kind": kind, "runs": runs, "boxes": int(len(out[0][0])),
+            "what": "Prediction minus network (sigmoid, hm2box, cat, NMS) on the host CPU, fp32, median wall time"}
 
 
 def run_reference(args):
@@ -153,22 +231,69 @@ def run_reference(args):
         return
     S, size, batch = args.num_stack, args.imsize, 2
     steps, warmup = max(1, min(args.steps, 30)), max(1, min(args.warmup, 3))
-    ips, dt, cores = time_cpu(torch, S, size, batch, steps, warmup)
-    cpu_name = ""
-    try:
-        cpu_name = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
-    except Exception:
-        pass
-    sample = (f"oracle port of the reference path (fp32 PyTorch CPU), {steps} timed steps of a bounded batch-{batch} "
-              f"sample of the 512x512 workload (fwd + loss + bwd), {cores} threads, {cpu_name}")
+    ips, dt, cores, kind = time_cpu(torch, S, size, batch, steps, warmup)
+    what = ("the UNMODIFIED reference modules (baseline/_ref: hourglass.StackedHourglass + loss.LossCalculator, "
+            "train.py:99-134 loop body)" if kind == "reference" else "oracle port of the reference path")
+    sample = (f"{what}, fp32 PyTorch CPU, {steps} timed steps of a bounded batch-{batch} "
+              f"sample of the 512x512 workload (fwd + loss + bwd), {cores} threads, {cpu_name()}")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "img/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{S}-stack hourglass, 2 classes, {size}x{size}, train fwd+bwd", "batch_per_step": batch},
-            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ library bar
+def library_bar(torch, dev, S, B, size, steps=6, warmup=3):
+    """The only perf comparator that matters: the reference's network executed by the libraries the
+    reference itself calls (nn.Conv2d -> cuDNN, nn.BatchNorm2d, ... hourglass.py:100-103) on THIS GPU, bf16 autocast
+    (train.py:97 with the dtype BASELINE names), cudnn.benchmark (train.py:34), same step (fwd + loss + bwd), same batch,
+    CUDA-event timed. NCHW (the reference as written) and channels_last (the best stock layout)."""
+    from baseline import torch_eager
+    from real_time_helmet_detection_b200.loss import LossCalculator
+    res = {"workload": f"{S}-stack hourglass, {size}x{size}, batch {B}, train fwd + loss + bwd, bf16 autocast, "
+                       "cudnn.benchmark", "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+    try:
+        net, kind = torch_eager.reference_network(S, None, dev)
+        net.train()
+        crit = torch_eager.reference_loss(dev) or LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0).to(dev)
+        res["kind"] = kind + (" (unmodified hourglass.py / loss.py from baseline/_ref)" if kind == "reference"
+                              else " (torch.nn.functional port over the same parameter tree; reference not staged)")
+        x, gts = synthetic_batch(torch, B, size, 0)
+        x, gts = x.to(dev), [g.to(dev) for g in gts]
+        torch.backends.cudnn.benchmark = True
+
+        def step(inp):
+            for p in net.parameters():
+                p.grad = None
+            torch_eager.train_loop_body(net, crit, inp, gts, autocast_dtype=torch.bfloat16)
+
+        for name in ("nchw", "channels_last"):
+            inp = x
+            if name == "channels_last":
+                net.to(memory_format=torch.channels_last)
+                inp = x.contiguous(memory_format=torch.channels_last)
+            for _ in range(warmup):
+                step(inp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step(inp)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"ms_per_step": ms, "img_s": B / ms * 1e3}
+        res["best_img_s"] = max(res["nchw"]["img_s"], res["channels_last"]["img_s"])
+    except Exception as exc:                      # e.g. out of memory on a shared box: keep the bench line alive
+        res["error"] = f"{type(exc).__name__}: {str(exc)[:200]}"
+    finally:
+        net = crit = None
+        torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -197,9 +322,20 @@ def dominant_kernel_roofline(torch, dev, peaks, reps=20):
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)", "us_per_launch": dt * 1e6,
             "flops_per_launch": flops,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
-            # (profiles/r01_conv_igemm_halo_ncu_full.txt); algorithmic bytes = 134.2 MB in + 134.2 MB out + 0.3 MB weights
-            "traffic": 226.6e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 268.7e6}
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from one `ncu --set full` capture,
+            # recorded (with the name of the capture's summary file) in profiles/conv_halo_traffic.json - a profiler
+            # figure cannot be taken inside a timed run; algorithmic bytes = 134.2 MB in + 134.2 MB out + 0.3 MB weights
+            **recorded_traffic(), "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 268.7e6}
+
+
+def recorded_traffic():
+    p = os.path.join(ROOT, "profiles", "conv_halo_traffic.json")
+    try:
+        d = json.load(open(p))
+        return {"traffic": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]),
+                "traffic_source": f"profiles/conv_halo_traffic.json <- {d['source']}"}
+    except Exception:
+        return {"traffic": None, "traffic_source": "profiles/conv_halo_traffic.json missing"}
 
 
 def decode_latency(torch, dev, S=1, runs=300):
@@ -256,7 +392,7 @@ def decode_latency(torch, dev, S=1, runs=300):
         wall.append(time.perf_counter() - t0)
     return {"workload": f"decode+NMS 512x512 batch 1, {S} stack, topk 100, conf 0.2, nms 0.2", "device_us": dev_us,
             "graph_replay_us": graph_us, "api_wall_us": statistics.median(wall) * 1e6, "boxes": int(b[0].shape[0]),
-            "algorithmic_bytes": 6 * H * W * 4 * S, "reference_cpu_us": "1450 (BASELINE.md, 8 vCPU Xeon, this container)"}
+            "algorithmic_bytes": 6 * H * W * 4 * S}
 
 
 def inference_latency(torch, dev, S=1, runs=50):
@@ -283,6 +419,45 @@ def inference_latency(torch, dev, S=1, runs=50):
     return {"workload": f"forward (eval) + decode + NMS, 512x512 batch 1, {S} stack, Prediction(cuda_graph=True)",
             "ms": ms, "fps": 1e3 / ms, "eager_ms": res["eager"],
             "reference": "README.md:76: 100 FPS (10 ms) on a GTX 1080 Ti, TorchScript C++ app"}
+
+
+def config3_line(torch, dev, peaks, steps=10, warmup=4):
+    """BASELINE.json configs[2] in the same run: 2-stack hourglass, 512x512, batch 16, bf16, train fwd + loss + bwd."""
+    from real_time_helmet_detection_b200.hourglass import StackedHourglass
+    from real_time_helmet_detection_b200.loss import LossCalculator
+    from real_time_helmet_detection_b200.train import train_step
+    S, B, size = 2, 16, 512
+    try:
+        torch.manual_seed(777)
+        net = StackedHourglass(S, 128, 6).to(dev).train()
+        crit = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0).to(dev)
+        x, gts = synthetic_batch(torch, B, size, 0)
+        x, gts = x.to(dev), [g.to(dev) for g in gts]
+
+        def step():
+            for p in net.parameters():
+                p.grad = None
+            train_step(net, crit, x, *gts)
+
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ips = B / ms * 1e3
+        return {"workload": "2-stack hourglass, 2 classes, 512x512, batch 16, bf16, train fwd + loss + bwd",
+                "value": ips, "unit": "img/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "step_frac_of_conv_roofline": ips * FLOPS_PER_IMG_TRAIN[2] / (peaks["bf16_tflops_sustained"] * 1e12)}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    finally:
+        net = None
+        torch.cuda.empty_cache()
 
 
 def run_ours(args):
@@ -434,11 +609,34 @@ def run_ours(args):
         dec = decode_latency(torch, dev, S=1)
         infer = inference_latency(torch, dev, S=1)
         cpu = None
+        lib = cfg3 = None
         if world == 1 and not args.no_cpu_baseline:
-            ips, dt, cores = time_cpu(torch, S, size, 2, 4, 1)
-            cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-                   "sample": "oracle port (fp32 PyTorch CPU restatement of the reference path), 4 timed steps of a "
-                             f"batch-2 sample of the 512x512 train fwd+loss+bwd workload, {cores} threads"}
+            # the reference path on this box's host cores, in the same run: a bounded batch-2 sample of the
+            # metric's own workload (512x512 train fwd+loss+bwd), config 1 exactly (128x128, batch 2, with / without
+            # Adam), and the decode of config 5
+            ips, dt, cores, kind = time_cpu(torch, S, size, 2, 6, 1)
+            arm1 = CpuArm(torch, 1)
+            c1 = time_cpu(torch, 1, 128, 2, 20, 3, adam=False, arm=arm1)
+            c1a = time_cpu(torch, 1, 128, 2, 20, 3, adam=True, arm=arm1)
+            what = ("unmodified reference modules from baseline/_ref (hourglass.py, loss.py, optim.py; train.py:99-136 "
+                    "loop body with the out-of-place squeeze)" if kind == "reference"
+                    else "oracle port (fp32 PyTorch CPU restatement of the reference path; reference not staged)")
+            cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": kind, "cpu": cpu_name(),
+                   "sample": f"{what}, 6 timed steps of a batch-2 sample of the 512x512 train fwd+loss+bwd workload, "
+                             f"{cores} threads",
+                   "config1": {"workload": "1-stack, 2 classes, 128x128, batch 2, fp32 CPU, 20 timed steps",
+                               "fwd_loss_bwd": {"img_s": c1[0], "ms_per_step": c1[1] * 1e3},
+                               "fwd_loss_bwd_adam": {"img_s": c1a[0], "ms_per_step": c1a[1] * 1e3}}}
+            dcpu = cpu_decode_us(torch, S=1)
+            dec["reference_cpu_us"] = dcpu["us"]
+            dec["reference_cpu"] = dcpu
+            cpu["decode_config5_us"] = dcpu["us"]
+        if world == 1 and not args.no_library_bar:
+            lib = library_bar(torch, dev, S, B, size)
+            if "best_img_s" in lib:
+                lib["ours_over_best_library"] = per_gpu / lib["best_img_s"]
+        if world == 1 and S == 1 and not args.no_config3:
+            cfg3 = config3_line(torch, dev, peaks)
         line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -460,6 +658,10 @@ def run_ours(args):
                 "inference_b1": infer}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if lib is not None:
+            line["library_bar"] = lib
+        if cfg3 is not None:
+            line["config3"] = cfg3
         if hook is not None:
             line["allreduce"] = {"calls_per_step": hook.calls / max(1, (warmup + 2 * args.steps + 2)),
                                  "bytes": hook.elements * 4}
@@ -479,6 +681,8 @@ def main():
     ap.add_argument("--imsize", type=int, default=512)
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

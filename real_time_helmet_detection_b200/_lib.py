@@ -110,8 +110,9 @@ def ptr(t) -> c_void_p | None:
     return c_void_p(t.data_ptr())
 
 
-def stream() -> c_void_p:
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None) -> c_void_p:
+    """The current torch stream of `device` (default: the current device)."""
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:

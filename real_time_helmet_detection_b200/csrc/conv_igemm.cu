@@ -397,12 +397,7 @@ template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kStages * (kABytes + BLOCK_N * 128) + 1024 /*align*/ + 256 /*barriers*/ +
                                2 * BLOCK_N * 4 + 8 * 2048 /*store staging*/;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr_set = true;
-    }
+    HD_ENSURE_DYN_SMEM(conv_igemm_kernel<BLOCK_N>, smem_bytes);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_kernel<BLOCK_N>, grid,
                                      BLOCK_N >= 64 ? 384 : kThreads,
@@ -661,12 +656,7 @@ static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligi
 
 static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 128 + 8 * 2048;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr_set = true;
-    }
+    HD_ENSURE_DYN_SMEM(conv_igemm_halo_kernel, smem_bytes);
     // store box of the transposed epilogue: 32 channels x 16 columns x 2 rows, dense (un-swizzled) in shared memory
     alignas(64) CUtensorMap to;
     uint64_t dims[4] = {(uint64_t)p.cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};

@@ -255,12 +255,7 @@ template <int BLOCK_N, bool HALO>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
     constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
     constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HALO ? 160 : 128) * BLOCK_N * 2 + 1024 + 256 + 4 * 4096;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, HALO>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_set = true;
-    }
+    HD_ENSURE_DYN_SMEM((conv_wgrad_kernel<BLOCK_N, HALO>), smem_bytes);
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HALO>,
                                      p.groups * p.ksplit,
                                      kWgThreads, smem_bytes, stream, tdy, tx, p));

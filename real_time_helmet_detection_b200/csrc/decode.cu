@@ -405,12 +405,7 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     dim3 grid((W + 31) / 32, (H + 7) / 8, static_cast<unsigned>(ps * C));
     HD_CHECK_CUDA(::hd::launch_k(decode_peaks_kernel, grid, dim3(32, 8), 0, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CHECK_CUDA(cudaFuncSetAttribute(decode_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kSelSmem)));
-        attr_set = true;
-    }
+    HD_ENSURE_DYN_SMEM(decode_select_nms_kernel, static_cast<int>(kSelSmem));
     HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, kSelThreads, kSelSmem, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;

@@ -37,7 +37,20 @@ encode_targets_kernel(const float* __restrict__ boxes, const int* __restrict__ l
     pdl_prologue();
     __shared__ EncBox s_box[kEncMaxBoxes];
     const int b = blockIdx.y;
-    for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = cell < h * w;
+    const int y = live ? cell / w : 0, x = live ? cell - y * w : 0;
+    float m[kEncMaxCls];
+    bool is_nan[kEncMaxCls];
+#pragma unroll
+    for (int c = 0; c < kEncMaxCls; ++c) { m[c] = 0.f; is_nan[c] = false; }
+    float mk = 0.f, ox = 0.f, oy = 0.f, sx = 0.f, sy = 0.f;
+    // any number of boxes per image (the reference's box2hm has no cap): chunks of kEncMaxBoxes through shared memory,
+    // in list order, so "the last box at a cell wins" (transform.py:25-37) is preserved across chunks
+    for (int j0 = 0; j0 < nmax; j0 += kEncMaxBoxes) {
+    const int nchunk = min(kEncMaxBoxes, nmax - j0);
+    for (int jj = threadIdx.x; jj < nchunk; jj += blockDim.x) {
+        const int j = j0 + jj;
         EncBox e;
         e.label = labels[static_cast<size_t>(b) * nmax + j];
         const float* bp = boxes + (static_cast<size_t>(b) * nmax + j) * 4;
@@ -66,19 +79,10 @@ encode_targets_kernel(const float* __restrict__ boxes, const int* __restrict__ l
             if (err && blockIdx.x == 0) atomicAdd(err, 1);    // every block of the image re-derives the boxes
             e.label = -1;
         }
-        s_box[j] = e;
+        s_box[jj] = e;
     }
     __syncthreads();
-
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= h * w) return;
-    const int y = cell / w, x = cell - y * w;
-    float m[kEncMaxCls];
-    bool is_nan[kEncMaxCls];
-#pragma unroll
-    for (int c = 0; c < kEncMaxCls; ++c) { m[c] = 0.f; is_nan[c] = false; }
-    float mk = 0.f, ox = 0.f, oy = 0.f, sx = 0.f, sy = 0.f;
-    for (int j = 0; j < nmax; ++j) {
+    for (int j = 0; live && j < nchunk; ++j) {
         const EncBox& e = s_box[j];
         if (e.label < 0) continue;
         const int dx = x - e.ix, dy = y - e.iy;
@@ -94,6 +98,9 @@ encode_targets_kernel(const float* __restrict__ boxes, const int* __restrict__ l
             }
         }
     }
+    __syncthreads();
+    }   // box chunks
+    if (!live) return;
     const size_t hw = static_cast<size_t>(h) * w;
 #pragma unroll
     for (int c = 0; c < kEncMaxCls; ++c)
@@ -140,7 +147,7 @@ extern "C" int hd_encode_targets(const float* boxes, const int* labels, int B, i
                                  int* err_count, cudaStream_t stream) {
     using namespace hd;
     HD_REQUIRE(B > 0 && h > 0 && w > 0, "encode_targets: empty output");
-    HD_REQUIRE(nmax >= 0 && nmax <= kEncMaxBoxes, "encode_targets: nmax=%d exceeds %d boxes per image", nmax, kEncMaxBoxes);
+    HD_REQUIRE(nmax >= 0, "encode_targets: nmax=%d", nmax);
     HD_REQUIRE(num_cls >= 1 && num_cls <= kEncMaxCls, "encode_targets: num_cls=%d unsupported (max %d)", num_cls, kEncMaxCls);
     HD_REQUIRE(scale_factor >= 1, "encode_targets: scale_factor=%d", scale_factor);
     HD_REQUIRE(heat && offset && size && mask && (nmax == 0 || (boxes && labels)), "encode_targets: null pointer");

@@ -131,13 +131,13 @@ void trace_dump() {
 }
 
 int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];      // per device (zero-initialised)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-        n = prop.multiProcessorCount;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 
 #define HD_OK 0
 #define HD_ERR_INVALID (-22)   // -EINVAL: bad shape / argument
@@ -29,6 +30,20 @@ int fail(int code, const char* fmt, ...);
 #define HD_REQUIRE(cond, ...)                                      \
     do {                                                           \
         if (!(cond)) return ::hd::fail(HD_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: remember it per call site and
+// device (bit i of the mask = device i), so that one process driving several GPUs opts in on each of them.
+#define HD_ENSURE_DYN_SMEM(kernel, bytes)                                                                    \
+    do {                                                                                                     \
+        static std::atomic<unsigned long long> _hd_done{0};                                                  \
+        int _hd_dev = 0;                                                                                     \
+        HD_CHECK_CUDA(cudaGetDevice(&_hd_dev));                                                              \
+        const unsigned long long _hd_bit = 1ull << (_hd_dev & 63);                                           \
+        if (!(_hd_done.load(std::memory_order_acquire) & _hd_bit)) {                                         \
+            HD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+            _hd_done.fetch_or(_hd_bit, std::memory_order_release);                                           \
+        }                                                                                                    \
     } while (0)
 
 // Encode a tiled bf16 tensor map with 128B swizzle and zero OOB fill.

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream
 
-MAX_BOXES = 128       # kEncMaxBoxes in csrc/encode.cu
+BOX_CHUNK = 128       # kEncMaxBoxes in csrc/encode.cu: boxes are processed in chunks of this size, any count works
 
 _NORMALIZERS = {      # utils.py:55-62 `get_normalizer`
     "imagenet": ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
@@ -47,7 +47,9 @@ def normalize_images(images_u8: torch.Tensor, pretrained: str = "imagenet", out:
         out = torch.empty(B, 3, H, W, device=images_u8.device, dtype=torch.float32)
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
-    check(_lib.lib().hd_normalize_u8(ptr(images_u8), ptr(out), B, H, W, m, s, stream()), "hd_normalize_u8")
+    with torch.cuda.device(images_u8.device):
+        check(_lib.lib().hd_normalize_u8(ptr(images_u8), ptr(out), B, H, W, m, s, stream(images_u8.device)),
+              "hd_normalize_u8")
     return out
 
 
@@ -74,9 +76,10 @@ def encode_targets(boxes: torch.Tensor, labels: torch.Tensor, imsize, scale_fact
     size = torch.empty(B, 2, h, w, device=dev, dtype=torch.float32)
     mask = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
     err = torch.zeros(1, device=dev, dtype=torch.int32) if return_errors else None
-    check(_lib.lib().hd_encode_targets(ptr(boxes), ptr(labels), B, nmax, h, w, num_cls, int(scale_factor),
-                                       int(bool(normalized)), ptr(heat), ptr(off), ptr(size), ptr(mask), ptr(err),
-                                       stream()), "hd_encode_targets")
+    with torch.cuda.device(dev):
+        check(_lib.lib().hd_encode_targets(ptr(boxes), ptr(labels), B, nmax, h, w, num_cls, int(scale_factor),
+                                           int(bool(normalized)), ptr(heat), ptr(off), ptr(size), ptr(mask), ptr(err),
+                                           stream(dev)), "hd_encode_targets")
     return (heat, off, size, mask, err) if return_errors else (heat, off, size, mask)
 
 
@@ -85,9 +88,7 @@ def pad_boxes(batch_bbs_lst: Sequence[Sequence], batch_id_lst: Sequence[Sequence
     `None` boxes are skipped like transform.py:15-16."""
     B = len(batch_bbs_lst)
     longest = max([len(b) for b in batch_bbs_lst] + [1])
-    nmax = longest if nmax is None else nmax
-    if longest > nmax or nmax > MAX_BOXES:
-        raise RuntimeError(f"{longest} boxes in one image: the device encoder takes at most {min(nmax, MAX_BOXES)}")
+    nmax = longest if nmax is None else max(nmax, longest)     # like box2hm, no cap on the boxes per image
     boxes = np.zeros((B, nmax, 4), np.float32)
     labels = np.full((B, nmax), -1, np.int32)
     for b, (bbs, ids) in enumerate(zip(batch_bbs_lst, batch_id_lst)):
@@ -102,7 +103,9 @@ def pad_boxes(batch_bbs_lst: Sequence[Sequence], batch_id_lst: Sequence[Sequence
 class DeviceCollate:
     """`collate_fn` tail on the device: (uint8 HWC images, box lists) -> the five training tensors on `device`.
 
-    Two pinned staging slots alternate, so batch i+1 can be staged while batch i's copy is still in flight."""
+    Two pinned staging slots alternate, so batch i+1 can be staged while batch i's copy is still in flight. `max_boxes`
+    is only the initial size of the pinned box slots: an image with more boxes grows them (the reference's
+    collate_fn / box2hm accept any number of boxes, and so does the encoder kernel)."""
 
     def __init__(self, device, num_cls: int = 2, normalized_coord: bool = False, pretrained: str = "imagenet",
                  scale_factor: int = 4, max_boxes: int = 32):
@@ -115,9 +118,11 @@ class DeviceCollate:
         self._slots = [None, None]
         self._turn = 0
 
-    def _slot(self, B, H, W):
+    def _slot(self, B, H, W, nbox):
+        if nbox > self.max_boxes:            # a crowded image: grow the box slots (rounded up, so this happens rarely)
+            self.max_boxes = (nbox + 31) // 32 * 32
         s = self._slots[self._turn]
-        if s is None or s["img"].shape != (B, H, W, 3):
+        if s is None or s["img"].shape != (B, H, W, 3) or s["box"].shape[1] != self.max_boxes:
             s = {"img": torch.empty(B, H, W, 3, dtype=torch.uint8).pin_memory(),
                  "box": torch.empty(B, self.max_boxes, 4, dtype=torch.float32).pin_memory(),
                  "lab": torch.empty(B, self.max_boxes, dtype=torch.int32).pin_memory(),
@@ -131,7 +136,7 @@ class DeviceCollate:
     def __call__(self, img_np_lst, batch_bbs_lst, batch_id_lst):
         B = len(img_np_lst)
         H, W = img_np_lst[0].shape[:2]
-        s = self._slot(B, H, W)
+        s = self._slot(B, H, W, max([len(b) for b in batch_bbs_lst] + [1]))
         img_host = s["img"].numpy()
         for b, im in enumerate(img_np_lst):
             img_host[b] = im

@@ -19,7 +19,9 @@ from .transform import _decode_call
 
 
 class _Captured:
-    __slots__ = ("graph", "x", "boxes", "clss", "scores", "counts")
+    # `workspace` pins the network's HBM arena the graph's kernels were recorded against: the graph bakes raw pointers
+    # into it, so it must neither be freed nor silently swapped while the graph can still be replayed
+    __slots__ = ("graph", "x", "boxes", "clss", "scores", "counts", "workspace")
 
 
 class Prediction(torch.nn.Module):
@@ -72,6 +74,9 @@ class Prediction(torch.nn.Module):
             raise RuntimeError("Prediction(cuda_graph=True) records the eval-mode forward: call network.eval() first")
         c = _Captured()
         c.x = x.detach().clone()
+        # a PRIVATE arena per graph: the recorded kernels keep raw pointers into it, so it must outlive every other
+        # forward of the network (other shapes, eager calls, training steps drop and re-allocate the network's own)
+        self.network._workspace, self.network._ws_key = None, None
         cur = torch.cuda.current_stream(x.device)
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(cur)
@@ -83,6 +88,7 @@ class Prediction(torch.nn.Module):
         c.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(c.graph), torch.no_grad():
             c.boxes, c.clss, c.scores, c.counts = self._decode_device(self.network(c.x))
+        c.workspace = self.network._workspace
         return c
 
     def forward(self, x):

@@ -327,6 +327,8 @@ class StackedHourglass(nn.Module):
     def _run_forward(self, x):
         L = _lib.lib()
         h = self._native()
+        if x.dtype != torch.float32:          # the stem kernel reads fp32 NCHW; never reinterpret another dtype's bytes
+            x = x.float()
         x = x.contiguous()
         B, _, H, W = x.shape
         self._check_params(x.device)
@@ -342,8 +344,9 @@ class StackedHourglass(nn.Module):
         logits = torch.empty((B, self.num_stack, self.out_ch, H // 4, W // 4), dtype=torch.float32, device=x.device)
         tab = self._build_table()
         self._generation += 1
-        check(L.hd_net_forward(h, tab, len(tab), ptr(x), ptr(logits), ptr(self._workspace), self._workspace.numel(),
-                               B, H, W, 1 if self.training else 0, stream()), "net_forward")
+        with torch.cuda.device(x.device):     # kernels, streams and per-device attributes follow the input's device
+            check(L.hd_net_forward(h, tab, len(tab), ptr(x), ptr(logits), ptr(self._workspace), self._workspace.numel(),
+                                   B, H, W, 1 if self.training else 0, stream(x.device)), "net_forward")
         return logits
 
     def _run_backward(self, dlogits):
@@ -353,8 +356,9 @@ class StackedHourglass(nn.Module):
         flat = torch.zeros((total,), dtype=torch.float32, device=dlogits.device)
         tab = self._build_table(flat)
         d = dlogits.contiguous().float()
-        check(L.hd_net_backward(self._handle, tab, len(tab), ptr(d), ptr(self._workspace), self._workspace.numel(),
-                                stream()), "net_backward")
+        with torch.cuda.device(d.device):
+            check(L.hd_net_backward(self._handle, tab, len(tab), ptr(d), ptr(self._workspace), self._workspace.numel(),
+                                    stream(d.device)), "net_backward")
         if self.grad_sync is not None:
             self.grad_sync(flat)
         self._flat_grad = flat

@@ -39,10 +39,11 @@ class _FusedLoss(torch.autograd.Function):
         ghm, goff, gsize, mask = (t.float().contiguous() for t in (ghm, goff, gsize, mask))
         B, C, H, W = hm.shape
         buf = torch.empty(10, dtype=torch.float32, device=hm.device)   # [0:5] results, [5:10] reduction scratch
-        check(_lib.lib().hd_loss_forward(ptr(hm), hm.stride(0), ptr(off), off.stride(0), ptr(size), size.stride(0),
-                                         ptr(ghm), ptr(goff), ptr(gsize), ptr(mask), B, C, H, W, alpha, beta, w_hm,
-                                         w_off, w_size, int(from_logits), int(sigmoid_reg), ptr(buf[5:]), ptr(buf),
-                                         stream()), "loss_forward")
+        with torch.cuda.device(hm.device):
+            check(_lib.lib().hd_loss_forward(ptr(hm), hm.stride(0), ptr(off), off.stride(0), ptr(size), size.stride(0),
+                                             ptr(ghm), ptr(goff), ptr(gsize), ptr(mask), B, C, H, W, alpha, beta, w_hm,
+                                             w_off, w_size, int(from_logits), int(sigmoid_reg), ptr(buf[5:]), ptr(buf),
+                                             stream(hm.device)), "loss_forward")
         ctx.save_for_backward(hm, off, size, ghm, goff, gsize, mask, buf)
         ctx.cfg = cfg
         values = buf[:4]
@@ -56,11 +57,12 @@ class _FusedLoss(torch.autograd.Function):
         B, C, H, W = hm.shape
         d_hm, d_off, d_size = torch.empty_like(hm), torch.empty_like(off), torch.empty_like(size)
         g = g_total.detach().float().contiguous()
-        check(_lib.lib().hd_loss_backward(ptr(hm), hm.stride(0), ptr(off), off.stride(0), ptr(size), size.stride(0),
-                                          ptr(ghm), ptr(goff), ptr(gsize), ptr(mask), B, C, H, W, alpha, beta, w_hm,
-                                          w_off, w_size, int(from_logits), int(sigmoid_reg), ptr(buf), ptr(g),
-                                          ptr(d_hm), d_hm.stride(0), ptr(d_off), d_off.stride(0), ptr(d_size),
-                                          d_size.stride(0), stream()), "loss_backward")
+        with torch.cuda.device(hm.device):
+            check(_lib.lib().hd_loss_backward(ptr(hm), hm.stride(0), ptr(off), off.stride(0), ptr(size), size.stride(0),
+                                              ptr(ghm), ptr(goff), ptr(gsize), ptr(mask), B, C, H, W, alpha, beta, w_hm,
+                                              w_off, w_size, int(from_logits), int(sigmoid_reg), ptr(buf), ptr(g),
+                                              ptr(d_hm), d_hm.stride(0), ptr(d_off), d_off.stride(0), ptr(d_size),
+                                              d_size.stride(0), stream(hm.device)), "loss_backward")
         return d_hm, d_off, d_size, None, None, None, None, None
 
 

@@ -90,10 +90,12 @@ class FusedAdam(optim.Adam):
             if used == 0:
                 continue
             beta1, beta2 = group["betas"]
-            check(_lib.lib().hd_adam_step(ctypes.cast(jobs, c_void_p), used, ptr(jobs_dev), chunk, float(group["lr"]),
-                                          float(beta1), float(beta2), float(group["eps"]), ptr(step_dev),
-                                          ptr(grad_scale) if grad_scale is not None else None,
-                                          ptr(found_inf) if found_inf is not None else None, stream()), "adam_step")
+            with torch.cuda.device(m.device):
+                check(_lib.lib().hd_adam_step(ctypes.cast(jobs, c_void_p), used, ptr(jobs_dev), chunk,
+                                              float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
+                                              ptr(step_dev), ptr(grad_scale) if grad_scale is not None else None,
+                                              ptr(found_inf) if found_inf is not None else None, stream(m.device)),
+                      "adam_step")
         return loss
 
     def state_dict(self):

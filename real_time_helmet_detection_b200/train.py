@@ -1,32 +1,58 @@
 """Training-step driver — the body of the reference's hot loop (train.py:92-139) over the B200 kernels.
 
 `train_step` is the call a user of this package makes per iteration: host (or device) batch in, scalar loss out,
-parameter gradients accumulated. It mirrors train.py:97-136: forward, per-stack split + head activation + loss
-(fused into one kernel per stack here), sum over stacks, optional GradScaler, backward, optional optimizer step.
-`load_network` mirrors train.py:164-201 for the pieces on the hot path (network + loss calculator factory).
+parameter gradients accumulated. It mirrors train.py:97-139: forward, per-stack split + head activation + loss
+(fused into one kernel per stack here), sum over stacks, optional GradScaler, backward, and - every `sub_divisions`
+iterations, the reference's gradient-accumulation flag (train.py:124) - the optimizer step + zero_grad.
+`load_network` is the factory of train.py:164-201 with the same 4-tuple return, DDP wrap and checkpoint-resume rules.
 """
 from __future__ import annotations
+
+import time
 
 import torch
 
 from .hourglass import StackedHourglass
 from .loss import LossCalculator
+from .optim import get_optimizer
 
 
 def load_network(args, device):
-    """Same argument names as the reference's argparse namespace (config.py); returns (network, loss_calculator)."""
-    network = StackedHourglass(num_stack=args.num_stack, in_ch=args.hourglass_inch, out_ch=args.num_cls + 4,
-                               increase_ch=args.increase_ch, activation=args.activation, pool=args.pool,
-                               neck_activation=args.neck_activation, neck_pool=args.neck_pool).to(device)
-    loss_calculator = LossCalculator(hm_weight=args.hm_weight, offset_weight=args.offset_weight,
-                                     size_weight=args.size_weight, focal_alpha=args.focal_alpha,
-                                     focal_beta=args.focal_beta).to(device)
-    return network, loss_calculator
+    """`args`: the reference's argparse namespace (config.py). Returns (network, optimizer, scheduler, loss_calculator)
+    exactly like train.py:164-201: optimizer / scheduler / loss calculator only with --train-flag, DistributedDataParallel
+    only for a multi-GPU training run, and `--model-load` restores network (+ optimizer, loss log, scheduler)."""
+    net_kwargs = dict(num_stack=args.num_stack, in_ch=args.hourglass_inch, out_ch=args.num_cls + 4,
+                      increase_ch=args.increase_ch, activation=args.activation, pool=args.pool,
+                      neck_activation=args.neck_activation, neck_pool=args.neck_pool)
+    network = StackedHourglass(**net_kwargs).to(device)
+    training = bool(getattr(args, "train_flag", False))
+    if training and len(getattr(args, "gpu_no", [0])) > 1:
+        network = torch.nn.parallel.DistributedDataParallel(network, device_ids=[device])
+    optimizer = scheduler = loss_calculator = None
+    if training:
+        optimizer, scheduler = get_optimizer(network=network, lr=args.lr, lr_milestone=args.lr_milestone,
+                                             lr_gamma=args.lr_gamma)
+        loss_calculator = LossCalculator(hm_weight=args.hm_weight, offset_weight=args.offset_weight,
+                                         size_weight=args.size_weight, focal_alpha=args.focal_alpha,
+                                         focal_beta=args.focal_beta).to(device)
+    path = getattr(args, "model_load", None)
+    if path:
+        ckpt = torch.load(path, map_location=device, weights_only=False)
+        network.load_state_dict(ckpt["state_dict"])
+        print("%s: Weights are loaded from %s" % (time.ctime(), path))
+        if training:
+            optimizer.load_state_dict(ckpt["optimizer"])
+            loss_calculator.log = ckpt["loss_log"]
+            if scheduler is not None:
+                scheduler.load_state_dict(ckpt["scheduler"])
+    return network, optimizer, scheduler, loss_calculator
 
 
 def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, gt_mask, num_cls=2,
-               normalized_coord=False, scaler=None, optimizer=None):
-    """One iteration of train.py:92-139. Tensors may live on the host (pinned for async copies) or the device."""
+               normalized_coord=False, scaler=None, optimizer=None, step=True):
+    """One iteration of train.py:92-139. Tensors may live on the host (pinned for async copies) or the device.
+    `step=False` accumulates gradients without touching the optimizer (the reference's `--sub-divisions`: pass
+    `step=(iteration % sub_divisions == 0)`)."""
     device = next(network.parameters()).device
     image = image.to(device, non_blocking=True)
     gts = [t.to(device, non_blocking=True) for t in (gt_heatmap, gt_offset, gt_size, gt_mask)]   # once, not per stack
@@ -35,16 +61,17 @@ def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, 
     for s in range(outputs.shape[1]):
         total_loss = total_loss + loss_calculator.forward_logits(outputs[:, s], *gts, num_cls=num_cls,
                                                                  normalized_coord=normalized_coord)
+    do_step = step and optimizer is not None
     if scaler is not None:
         scaler.scale(total_loss).backward()
-        if optimizer is not None:
+        if do_step:
             scaler.step(optimizer)
             scaler.update()
     else:
         total_loss.backward()
-        if optimizer is not None:
+        if do_step:
             optimizer.step()
-    if optimizer is not None:
+    if do_step:
         optimizer.zero_grad(set_to_none=True)
     return total_loss.detach()
 

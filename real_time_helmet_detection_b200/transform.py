@@ -30,10 +30,11 @@ def _decode_call(heat, off, wh, strides, B, S, C, H, W, topk, scale_factor, conf
         raise RuntimeError("selected index k out of range")
     boxes, clss, scores, counts, scratch = bufs if bufs is not None else _decode_buffers(heat.device, B, S, C, H, W, topk)
     (bh, sh), (bo, so), (bw, sw) = strides
-    check(L.hd_decode_nms(ptr(heat), bh, sh, ptr(off), bo, so, ptr(wh), bw, sw, B, S, C, H, W, int(topk),
-                          float(scale_factor), float(conf_th), float(nms_th), int(bool(normalized)),
-                          int(bool(apply_sigmoid)), int(bool(do_nms)), ptr(scratch), ptr(boxes), ptr(clss),
-                          ptr(scores), ptr(counts), stream()), "decode_nms")
+    with torch.cuda.device(heat.device):
+        check(L.hd_decode_nms(ptr(heat), bh, sh, ptr(off), bo, so, ptr(wh), bw, sw, B, S, C, H, W, int(topk),
+                              float(scale_factor), float(conf_th), float(nms_th), int(bool(normalized)),
+                              int(bool(apply_sigmoid)), int(bool(do_nms)), ptr(scratch), ptr(boxes), ptr(clss),
+                              ptr(scores), ptr(counts), stream(heat.device)), "decode_nms")
     return boxes, clss, scores, counts
 
 

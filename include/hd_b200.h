@@ -285,6 +285,13 @@ int hd_net_forward(hd_net* net, const hd_unit_ptrs* units, int n_units, const fl
 /* Autograd of the above: dlogits (B,S,out_ch,H/4,W/4) fp32 -> all parameter gradients (units[i].d*). */
 int hd_net_backward(hd_net* net, const hd_unit_ptrs* units, int n_units, const float* dlogits, void* workspace,
                     size_t workspace_bytes, hd_stream_t stream);
+/* The same pass in two calls - the hook for DistributedDataParallel's overlap of the gradient exchange with backward
+ * (train.py:174-175; the reducer all-reduces finished buckets while autograd still runs): stage 1 enqueues the backward
+ * of the stacks (head, neck, hourglass) and, if comm_stream != NULL, makes comm_stream wait until every parameter
+ * gradient of those units is complete, so the caller can enqueue its collective there; stage 2 (same arguments)
+ * enqueues the PreLayer backward and joins the library's internal streams into `stream`. */
+int hd_net_backward_stage(hd_net* net, const hd_unit_ptrs* units, int n_units, const float* dlogits, void* workspace,
+                          size_t workspace_bytes, hd_stream_t stream, int stage, hd_stream_t comm_stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,11 @@ struct hd_net {
         bf16 *x_in, *hg_out, *Yn, *F1, *F2, *pred64, *T;
     };
     std::vector<StackSaved> stacks;
+    // staged backward (hd_net_backward_stage): stage 1 = the stacks (head, neck, hourglass), stage 2 = PreLayer + join.
+    // `dX_pre` carries the gradient w.r.t. the PreLayer output across the stage boundary.
+    bf16* dX_pre = nullptr;
+    int bwd_stage = 0;                      // 0: no backward in flight, 1: stage 1 enqueued
+    cudaStream_t side_keep = nullptr;
     void* wgrad_ws = nullptr;
     size_t wgrad_ws_bytes = 0;
     float* small = nullptr;   // scratch for BN-backward sums / coefficients
@@ -718,14 +723,19 @@ static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const b
     n->bw.off = mark;
 }
 
-static void backward_impl(hd_net* n, const float* dlogits) {
+// stages: bit 0 = the stacks (head / neck / hourglass of every stack, last to first), bit 1 = PreLayer + stream join.
+// Every parameter gradient of the stacks - ~82 % of the flat gradient buffer for one stack, ~90 % for two - is complete
+// (on the side stream for the weights, on the caller's stream for BN / bias gradients) when stage 1 has been enqueued,
+// ~3 ms before the backward pass ends: that is where the data-parallel exchange of that bucket starts (parallel.py).
+static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
     const int B = n->B, C = n->in_ch;
-    phase_mark(n, "(loss)bwd:start");
     const int H2 = n->H / 2, W2 = n->W / 2, H4 = n->H / 4, W4 = n->W / 4;
     const size_t full4 = act_bytes(B, H4, W4, C);
     const long long hw4 = static_cast<long long>(H4) * W4;
     const long long npix4 = static_cast<long long>(B) * hw4;
     bf16* dXn = nullptr;  // gradient w.r.t. the input of stack i+1
+    if (stages & 1) {
+    phase_mark(n, "(loss)bwd:start");
     for (int i = n->S - 1; i >= 0; --i) {
         hd_net::StackSaved& s = n->stacks[i];
         const bool merge = i < n->S - 1;
@@ -776,6 +786,10 @@ static void backward_impl(hd_net* n, const float* dlogits) {
         phase_mark(n, "hourglass bwd");
         dXn = dXi;
     }
+    n->dX_pre = dXn;
+    }   // stage 1
+    if (!(stages & 2)) return;
+    dXn = n->dX_pre;
     // PreLayer
     bf16* dR3 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
     residual_bwd(n, n->r_pre4, dXn, dR3, B);
@@ -905,14 +919,13 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
     return n->rc;
 }
 
-extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* dlogits,
-                               void* workspace, size_t workspace_bytes, hd_stream_t stream) {
+static int backward_begin(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* dlogits, void* workspace,
+                          size_t workspace_bytes, hd_stream_t stream) {
     HD_REQUIRE(n && units && dlogits && workspace, "net_backward: null argument");
     HD_REQUIRE(n_units == static_cast<int>(n->units.size()), "net_backward: unit table size mismatch");
     HD_REQUIRE(n->trained_fwd, "net_backward: no training-mode forward pass is pending on this network");
+    HD_REQUIRE(n->bwd_stage == 0, "net_backward: a staged backward pass is already in flight (call stage 2 first)");
     HD_REQUIRE(reinterpret_cast<uint8_t*>(workspace) == n->persist.base, "net_backward: workspace moved since the forward pass");
-    static const int train_pdl = getenv("HD_TRAIN_PDL") ? atoi(getenv("HD_TRAIN_PDL")) : 0;
-    PdlScope pdl(train_pdl);
     n->up = units; n->stream = stream; n->rc = 0;
     if (!n->side) {
         // The weight-gradient stream gets the highest priority: its kernels (wgrad, and above all the tiny split-K
@@ -925,7 +938,7 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
             return fail(HD_ERR_CUDA, "net_backward: cannot create the weight-gradient stream");
     }
     static const bool serial = getenv("HD_SERIAL_WGRAD") != nullptr;   // debug knob: wgrad on the main stream
-    cudaStream_t side_keep = n->side;
+    n->side_keep = n->side;
     if (serial) n->side = stream;
     if (!n->alt_stream && cudaStreamCreateWithFlags(&n->alt_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(HD_ERR_CUDA, "net_backward: cannot create the second lane's stream");
@@ -943,11 +956,61 @@ extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units
     n->wg = Arena(); n->wg.base = region; n->wg.cap = region_cap;
     n->bw = Arena(); n->bw.base = region + wg_need; n->bw.cap = bw_need;
     n->alt.bw = Arena(); n->alt.bw.base = region + wg_need + bw_need; n->alt.bw.cap = alt_need;
-    HD_REQUIRE(wg_need + bw_need + alt_need <= region_cap,
-               "net_backward: workspace too small for the backward pass (%zu < %zu bytes)", region_cap,
-               wg_need + bw_need + alt_need);
-    backward_impl(n, dlogits);
-    n->side = side_keep;
+    if (wg_need + bw_need + alt_need > region_cap) {
+        n->side = n->side_keep;
+        return fail(HD_ERR_INVALID, "net_backward: workspace too small for the backward pass (%zu < %zu bytes)", region_cap,
+                    wg_need + bw_need + alt_need);
+    }
+    (void)workspace_bytes;
+    return HD_OK;
+}
+
+static void backward_end(hd_net* n) {
+    n->side = n->side_keep;
     n->trained_fwd = false;
+    n->bwd_stage = 0;
+}
+
+extern "C" int hd_net_backward(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* dlogits,
+                               void* workspace, size_t workspace_bytes, hd_stream_t stream) {
+    static const int train_pdl = getenv("HD_TRAIN_PDL") ? atoi(getenv("HD_TRAIN_PDL")) : 0;
+    PdlScope pdl(train_pdl);
+    int rc = backward_begin(n, units, n_units, dlogits, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    backward_impl(n, dlogits, 3);
+    backward_end(n);
+    return n->rc;
+}
+
+// The same pass in two calls, for callers that start the data-parallel exchange of the stacks' gradients while the
+// PreLayer backward (the 256x256 level: ~3 ms of a 12 ms step) is still running. Stage 1 enqueues the stacks and, when
+// `comm_stream` is given, makes it wait for everything that produced their parameter gradients (the caller's stream and
+// the internal weight-gradient stream) - the caller then enqueues its collective on `comm_stream`. Stage 2 enqueues the
+// PreLayer and joins the internal streams into `stream`.
+extern "C" int hd_net_backward_stage(hd_net* n, const hd_unit_ptrs* units, int n_units, const float* dlogits,
+                                     void* workspace, size_t workspace_bytes, hd_stream_t stream, int stage,
+                                     hd_stream_t comm_stream) {
+    static const int train_pdl = getenv("HD_TRAIN_PDL") ? atoi(getenv("HD_TRAIN_PDL")) : 0;
+    PdlScope pdl(train_pdl);
+    HD_REQUIRE(stage == 1 || stage == 2, "net_backward_stage: stage=%d", stage);
+    if (stage == 1) {
+        int rc = backward_begin(n, units, n_units, dlogits, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        backward_impl(n, dlogits, 1);
+        if (n->rc == 0 && comm_stream) {
+            cudaEvent_t em = next_event(n), es = next_event(n);
+            if (!em || !es || cudaEventRecord(em, n->stream) != cudaSuccess || cudaEventRecord(es, n->side) != cudaSuccess ||
+                cudaStreamWaitEvent(comm_stream, em, 0) != cudaSuccess || cudaStreamWaitEvent(comm_stream, es, 0) != cudaSuccess)
+                n->rc = fail(HD_ERR_CUDA, "net_backward_stage: cannot order the communication stream");
+        }
+        if (n->rc != 0) { backward_end(n); return n->rc; }
+        n->bwd_stage = 1;
+        return HD_OK;
+    }
+    HD_REQUIRE(n && n->bwd_stage == 1, "net_backward_stage: stage 2 without a pending stage 1");
+    HD_REQUIRE(stream == n->stream && units == n->up, "net_backward_stage: stage 2 must use the stream / unit table of stage 1");
+    n->rc = 0;
+    backward_impl(n, dlogits, 2);
+    backward_end(n);
     return n->rc;
 }

@@ -50,6 +50,8 @@ _lib.register("hd_net_workspace_bytes", c_size_t, [c_void_p, c_int, c_int, c_int
 _lib.register("hd_net_forward", c_int, [c_void_p, POINTER(UnitPtrs), c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                          c_int, c_int, c_int, c_int, c_void_p])
 _lib.register("hd_net_backward", c_int, [c_void_p, POINTER(UnitPtrs), c_int, c_void_p, c_void_p, c_size_t, c_void_p])
+_lib.register("hd_net_backward_stage", c_int, [c_void_p, POINTER(UnitPtrs), c_int, c_void_p, c_void_p, c_size_t, c_void_p,
+                                               c_int, c_void_p])
 
 
 def _container_forward(self, *args, **kwargs):
@@ -241,7 +243,9 @@ class StackedHourglass(nn.Module):
         self._table_key = None
         self._generation = 0
         self._flat_grad = None
-        self.grad_sync = None          # optional callable(flat_grad) run inside backward (parallel.FlatAllReduce)
+        # optional gradient exchange run inside backward (parallel.FlatAllReduce): either a plain callable(flat_grad)
+        # invoked after the whole pass, or an object with early(bucket) / late(bucket) for the two-bucket overlap
+        self.grad_sync = None
 
     # ------------------------------------------------------------------ unit table
     def units(self):
@@ -356,11 +360,24 @@ class StackedHourglass(nn.Module):
         flat = torch.zeros((total,), dtype=torch.float32, device=dlogits.device)
         tab = self._build_table(flat)
         d = dlogits.contiguous().float()
+        sync = self.grad_sync
         with torch.cuda.device(d.device):
-            check(L.hd_net_backward(self._handle, tab, len(tab), ptr(d), ptr(self._workspace), self._workspace.numel(),
-                                    stream(d.device)), "net_backward")
-        if self.grad_sync is not None:
-            self.grad_sync(flat)
+            if sync is not None and getattr(sync, "overlap", False) and sync.active():
+                # two buckets: the stacks' gradients (the tail of the flat buffer: parameters() lists pre_layer first)
+                # are exchanged on a communication stream while the PreLayer backward still runs; PreLayer's own
+                # gradients follow after the last weight-gradient kernel
+                n_pre = sum(p.numel() for p in self.pre_layer.parameters())
+                comm = sync.comm_stream(d.device)
+                args = (self._handle, tab, len(tab), ptr(d), ptr(self._workspace), self._workspace.numel(), stream(d.device))
+                check(L.hd_net_backward_stage(*args, 1, c_void_p(comm.cuda_stream)), "net_backward_stage(1)")
+                sync.early(flat[n_pre:], comm)
+                check(L.hd_net_backward_stage(*args, 2, None), "net_backward_stage(2)")
+                sync.late(flat[:n_pre])
+            else:
+                check(L.hd_net_backward(self._handle, tab, len(tab), ptr(d), ptr(self._workspace),
+                                        self._workspace.numel(), stream(d.device)), "net_backward")
+                if sync is not None:
+                    sync(flat)
         self._flat_grad = flat
         grads, off = [], 0
         for p in params:

@@ -12,6 +12,13 @@ def _worker(rank, world, port, q):
     flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
     hook = FlatAllReduce()
     hook(flat)
+    # the two-bucket protocol StackedHourglass._run_backward drives (early: stacks' tail of the buffer, late: PreLayer head)
+    flat2 = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    hook2 = FlatAllReduce()
+    assert hook2.overlap and hook2.active()
+    hook2.early(flat2[4:], None)
+    hook2.late(flat2[:4])
+    assert flat2.tolist() == [1.5 * i for i in range(10)] and hook2.calls == 2 and hook2.elements == 10 and hook2.steps == 1
     lin = torch.nn.Linear(3, 2)
     with torch.no_grad():
         lin.weight.fill_(float(rank + 5))

@@ -1,6 +1,7 @@
-"""2-GPU test of the data-parallel path: one process per GPU, batch sharded, ONE flat NCCL all-reduce of the gradient
-buffer inside the backward node. The averaged gradients must equal the mean of the two single-GPU gradients
-(per-replica BatchNorm, like the reference's DDP: train.py:174-175)."""
+"""2-GPU test of the data-parallel path: one process per GPU, batch sharded, the flat gradient buffer averaged over NCCL
+inside the backward node - as two overlapped buckets (stacks early on a communication stream, PreLayer at the end;
+the default) or as one flat all-reduce (overlap=False). The averaged gradients must equal the mean of the two ranks'
+local gradients (per-replica BatchNorm, like the reference's DDP: train.py:174-175)."""
 import os
 import pytest
 import torch
@@ -45,15 +46,29 @@ def _worker(rank, world, port, q):
             self.local = flat.clone()
             super().__call__(flat)
 
-    hook = Probe()
-    net.grad_sync = hook
-    synced = _grads_for(net, crit, x_all[shard].to(dev), [t[shard].to(dev) for t in gts_all])
-    locals_ = [torch.empty_like(hook.local) for _ in range(world)]
-    dist.all_gather(locals_, hook.local)
-    mean = (locals_[0] + locals_[1]) / 2
-    err = ((synced - mean).norm() / mean.norm()).item()                 # exact up to fp32 rounding
-    drift = ((hook.local - singles[rank]).norm() / singles[rank].norm()).item()   # run-to-run noise of one shard
-    q.put((rank, err, hook.calls, hook.elements, synced[:1000].cpu(), drift))
+        def early(self, bucket, comm):
+            with torch.cuda.stream(comm):                # comm is already ordered after the bucket's producers
+                self.local_tail = bucket.clone()
+            super().early(bucket, comm)
+
+        def late(self, bucket):
+            self.local_head = bucket.clone()
+            super().late(bucket)
+
+    out = []
+    for overlap in (False, True):
+        hook = Probe(overlap=overlap)
+        net.grad_sync = hook
+        synced = _grads_for(net, crit, x_all[shard].to(dev), [t[shard].to(dev) for t in gts_all])
+        torch.cuda.synchronize()
+        local = torch.cat([hook.local_head, hook.local_tail]) if overlap else hook.local
+        locals_ = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(locals_, local)
+        mean = (locals_[0] + locals_[1]) / 2
+        err = ((synced - mean).norm() / mean.norm()).item()                 # exact up to fp32 rounding
+        drift = ((local - singles[rank]).norm() / singles[rank].norm()).item()   # run-to-run noise of one shard
+        out.append((err, hook.calls, hook.elements, synced[:1000].cpu(), drift, hook.steps))
+    q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,11 +86,14 @@ def test_flat_allreduce_two_gpus():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, err, calls, elements, head, drift in res:
-        assert calls == 1 and elements == 4984070          # exactly one all-reduce of the flat 19.94 MB buffer
-        assert err < 1e-5, err                              # synced == mean of the two ranks' local gradients
-        assert drift < 0.5, drift                           # same shard, second run: only reduction-order noise
-    assert torch.equal(res[0][4], res[1][4])                # both ranks hold identical averaged gradients
+    for rank, out in res:
+        for overlap, (err, calls, elements, head, drift, steps) in zip((False, True), out):
+            # one flat all-reduce of the 19.94 MB buffer, or its two buckets (stacks + PreLayer)
+            assert calls == (2 if overlap else 1) and elements == 4984070 and steps == 1, (overlap, calls, elements)
+            assert err < 1e-5, (overlap, err)               # synced == mean of the two ranks' local gradients
+            assert drift < 0.5, drift                       # same shard, second run: only reduction-order noise
+    for i in range(2):
+        assert torch.equal(res[0][1][i][3], res[1][1][i][3])   # both ranks hold identical averaged gradients
 
 
 def _worker_torch_ddp(rank, world, port, q):

@@ -127,6 +127,14 @@ int hd_conv2d_igemm_vtaps(const void* x, const void* w_packed, void* out, const 
                           int out_cs, const hd_bn_fuse* bn, const float* scale, const float* shift, int relu,
                           hd_stream_t stream);
 
+/* Two convolutions summed in one pass: out = conv_{ksize x ksize}(x; w_packed) + conv_{1x1}(x2; w2_packed) (+ addend), all
+ * NHWC bf16, 64 output channels on a map with >= #SM 16x16 tiles. In the backward pass of `Residual(64, 128)`
+ * (hourglass.py:111-127, PreLayer's 256x256 level) this is dX = dgrad(conv1) + dgrad(skip): the 1x1 skip-branch gradient
+ * enters the 3x3 dgrad as one extra tap, so the intermediate tensor and the second launch disappear. */
+int hd_conv2d_igemm_dual(const void* x, const void* w_packed, const void* x2, const void* w2_packed, void* out,
+                         const void* addend, int N, int H, int W, int cin, int cin2, int cout, int block_n, int ksize,
+                         int out_cs, hd_stream_t stream);
+
 /* Backward of the 1x1 prediction head (hourglass.py:189-195). dw/dbias are accumulated into. */
 int hd_head_backward(const float* dlogits, long long batch_stride, const void* extra, int extra_cs, const void* feat,
                      const void* w_packed, void* dfeat, float* dw, float* dbias, int N, int H, int W, int cout,

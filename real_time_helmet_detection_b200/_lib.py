@@ -29,6 +29,7 @@ _SIGNATURES = {
     "hd_trace_dump": (None, []),
     "hd_conv2d_igemm": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "hd_conv2d_igemm_affine": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "hd_conv2d_igemm_dual": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "hd_bn_fold_all": (I, [P, I, P, P]),
     "hd_set_conv_variant": (None, [I]),
     "hd_set_conv_debug": (None, [I]),

@@ -57,6 +57,8 @@ struct ConvParams {
     const float* ep_scale; const float* ep_shift; int ep_relu;
     int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
                               // 2 = MMA issue skipped (halo kernel only)
+    int x2_chunks;            // N=64 halo kernel only: 64-channel chunks of a SECOND input that enters as one extra 1x1
+                              // tap (out += W2 * x2): the 1x1 skip-branch dgrad fused into the 3x3 dgrad of a Residual
 };
 
 // Sum v[0..31] across the 32 lanes of the warp; on return lane l holds the total of element l.
@@ -651,6 +653,254 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Halo kernel for 64 OUTPUT channels on the large maps (the 256x256 level of PreLayer: the 7x7 stem as four vertical
+// taps over the space-to-depth image, hourglass.py:163, and the dgrad of `Residual(64, 128)`, hourglass.py:164).
+// The generic kernel above is L2->SM bound there (every tap re-fetches its 128-pixel activation tile: 7 GB of operand
+// traffic for the 3x3 128->64 dgrad at 256^2 x B32, 455 us = 0.39 of the tensor peak) and the transposed halo kernel
+// would run the tensor core at half rate (M = 64). Here pixels are M again: a CTA tile is 16x16 pixels = two 128-row
+// accumulators of 64 fp32 columns; per (dx, 64-channel chunk) ONE activation box of (16 + kh - 1) rows x 16 columns is
+// loaded and the kh vertical taps / the two pixel halves are row offsets into it (dy*2048 B / 16 KB: whole swizzle groups).
+// Optionally a second input enters as an extra 1x1 tap (x2_chunks): dX = dgrad3x3(dY1) + dgrad1x1(dYs) in ONE pass -
+// the intermediate tensor and the second launch of the unfused pair disappear.
+// Epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves; a warp owns 32 channels of 2 x 32 pixels per tile, so the
+// BN statistics are per-lane running sums over all tiles (64 registers) with ONE transposing reduction per CTA, and the
+// bf16 NHWC output leaves through a 64B-swizzled staging tile and a TMA store (conflict-free STS, fully coalesced lines).
+constexpr int kN64ARows = 19 * 16;                 // up to 4 vertical taps: 16 + 3 box rows
+constexpr int kN64ABytes = kN64ARows * 128;        // 38,912 (a multiple of 1024)
+constexpr int kN64AStages = 3;
+constexpr int kN64BBytes = 64 * 128;               // one (tap, 64-channel chunk) weight tile for 64 output channels
+constexpr int kN64BStages = 6;
+constexpr int kN64Threads = 384;
+
+__global__ void __launch_bounds__(kN64Threads, 1)
+conv_igemm_n64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ CUtensorMap tmap_w2,
+                      const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
+    pdl_launch_dependents();
+    constexpr int BLOCK_N = 64;
+    constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 0, 0);    // M = 128 pixels, N = 64 channels
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kN64AStages * kN64ABytes;
+    uint8_t* s_stage = smem_b + kN64BStages * kN64BBytes;          // [8 warps][2 halves][2 KB], 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 8 * 2 * 2048);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kN64AStages;
+    uint64_t* b_full = a_empty + kN64AStages;
+    uint64_t* b_empty = b_full + kN64BStages;
+    uint64_t* tmem_full = b_empty + kN64BStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);       // [2][64]
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_o);
+        if (p.x2_chunks) { tma_prefetch_desc(&tmap_x2); tma_prefetch_desc(&tmap_w2); }
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < kN64AStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kN64BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);                     // 2 accumulator sets x 2 pixel halves x 64 columns
+    if (threadIdx.x < 2 * BLOCK_N) s_stat[threadIdx.x] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    const uint32_t a_bytes = static_cast<uint32_t>(16 + p.kh - 1) * 16u * 128u;
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int n = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * 16, y0 = ty * 16;
+                for (int dx = 0; dx < p.kw; ++dx) {
+                    for (int ck = 0; ck < p.cin_chunks; ++ck) {
+                        mbar_wait(&a_empty[sa], pa ^ 1);
+                        mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                        tma_load_4d(smem_a + sa * kN64ABytes, &tmap_x, &a_full[sa], ck * 64, x0 + dx - p.pad_x, y0 - p.pad_y, n);
+                        for (int dy = 0; dy < p.kh; ++dy) {
+                            mbar_wait(&b_empty[sb], pb ^ 1);
+                            mbar_arrive_expect_tx(&b_full[sb], kN64BBytes);
+                            tma_load_3d(smem_b + sb * kN64BBytes, &tmap_w, &b_full[sb], ck * 64, 0, dy * p.kw + dx);
+                            if (++sb == kN64BStages) { sb = 0; pb ^= 1; }
+                        }
+                        if (++sa == kN64AStages) { sa = 0; pa ^= 1; }
+                    }
+                }
+                for (int ck = 0; ck < p.x2_chunks; ++ck) {         // the fused 1x1 input: a 16-row box, one tap
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    mbar_arrive_expect_tx(&a_full[sa], 16u * 16u * 128u);
+                    tma_load_4d(smem_a + sa * kN64ABytes, &tmap_x2, &a_full[sa], ck * 64, x0, y0, n);
+                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    mbar_arrive_expect_tx(&b_full[sb], kN64BBytes);
+                    tma_load_3d(smem_b + sb * kN64BBytes, &tmap_w2, &b_full[sb], ck * 64, 0, 0);
+                    if (++sb == kN64BStages) { sb = 0; pb ^= 1; }
+                    if (++sa == kN64AStages) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 128;
+            bool first = true;
+            const int groups = p.kw * p.cin_chunks + p.x2_chunks;
+            for (int g = 0; g < groups; ++g) {
+                const int ntaps = g < p.kw * p.cin_chunks ? p.kh : 1;
+                mbar_wait(&a_full[sa], pa);
+                const uint32_t x_addr = smem_u32(smem_a + sa * kN64ABytes);
+                for (int dy = 0; dy < ntaps; ++dy) {
+                    mbar_wait(&b_full[sb], pb);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t wdesc = umma_smem_desc_sw128(smem_u32(smem_b + sb * kN64BBytes), 0, 1024);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            // 128 pixel rows of the box: tile rows 8h .. 8h+7, shifted dy rows down
+                            const uint64_t xdesc = umma_smem_desc_sw128(x_addr + (dy + 8 * h) * 2048, 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem + h * 64, xdesc + 2 * k, wdesc + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+                        }
+                        umma_commit(&b_empty[sb]);
+                    }
+                    __syncwarp();
+                    first = false;
+                    if (++sb == kN64BStages) { sb = 0; pb ^= 1; }
+                }
+                if (elect_one()) umma_commit(&a_empty[sa]);
+                __syncwarp();
+                if (++sa == kN64AStages) { sa = 0; pa ^= 1; }
+            }
+            if (elect_one()) umma_commit(&tmem_full[acc]);
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;                       // TMEM lane quarter: pixels 32*ew .. 32*ew+31 of a 128-pixel half
+        const int cw = (warp - 4) >> 2;                // column half: channels 32*cw .. 32*cw+31
+        const int cbase = cw * 32;
+        const bool do_stats = p.stat_sum != nullptr;
+        uint8_t* stage0 = s_stage + (warp - 4) * 4096;
+        float bias[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias[i] = (p.bias && cbase + i < p.cout) ? __ldg(p.bias + cbase + i) : 0.f;
+        float rs1[32], rs2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+        const int prow = (ew * 32 + static_cast<int>(lane)) >> 4, pcol = static_cast<int>(lane) & 15;   // within the half
+        const uint32_t swz = (lane >> 1) & 3u;         // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int n = tile / (p.tiles_x * p.tiles_y);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 128 + h * 64 + cbase, r);
+                const int y = ty * 16 + 8 * h + prow, x = tx * 16 + pcol;
+                const bool valid = y < p.H && x < p.W;
+                uint4 add[4];
+                if (p.addend) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) add[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(
+                            p.addend + ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.out_cs + cbase);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) add[q] = __ldg(ap + q);
+                    }
+                }
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + bias[i];
+                if (p.ep_scale) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], __ldg(p.ep_scale + cbase + i), __ldg(p.ep_shift + cbase + i));
+                }
+                if (p.addend) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&add[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __bfloat1622float2(hh[j]);
+                            v[q * 8 + 2 * j] += f.x;
+                            v[q * 8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                if (p.ep_relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (do_stats && valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        rs1[i] += v[i];
+                        rs2[i] = fmaf(v[i], v[i], rs2[i]);
+                    }
+                }
+                // staging tile [32 pixels][32 channels] bf16, 64-byte rows in the SWIZZLE_64B pattern of the store map
+                uint8_t* stage = stage0 + h * 2048;
+                if (lane == 0) bulk_wait_group_read<1>();      // the store that last read THIS buffer (two tiles... one tile ago) is done
+                __syncwarp();
+                if (p.dbg != 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                        u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                        u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                        u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                        *reinterpret_cast<uint4*>(stage + lane * 64 + ((static_cast<uint32_t>(q) ^ swz) << 4)) = u;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&tmap_o, stage, cbase, tx * 16, ty * 16 + 8 * h + 2 * ew, n);   // clipped at the border
+                        bulk_commit_group();
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+        if (lane == 0) bulk_wait_group<0>();           // all output tiles written before the CTA retires
+        if (do_stats) {
+            const float t1 = warp_transpose_reduce(rs1, lane), t2 = warp_transpose_reduce(rs2, lane);
+            atomicAdd(&s_stat[cbase + lane], t1);
+            atomicAdd(&s_stat[BLOCK_N + cbase + lane], t2);
+            flush_stats<BLOCK_N>(p, s_stat, static_cast<int>(threadIdx.x) - 128, 256, reinterpret_cast<int*>(tmem_slot + 1));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
 static int g_conv_debug = 0;
 static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible
 
@@ -662,12 +912,29 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
     uint64_t dims[4] = {(uint64_t)p.cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
     uint64_t str[3] = {(uint64_t)p.out_cs * 2, (uint64_t)p.W * p.out_cs * 2, (uint64_t)p.H * p.W * p.out_cs * 2};
     uint32_t box[4] = {32, 16, 2, 1};
-    int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle128=*/false);
+    int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle_bytes=*/0);
     if (rc) return rc;
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes,
                                      stream, tx, tw,
                                      to, p));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+static int launch_conv_n64(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const CUtensorMap& tw2,
+                           const ConvParams& p, cudaStream_t stream) {
+    constexpr int smem_bytes = kN64AStages * kN64ABytes + kN64BStages * kN64BBytes + 8 * 2 * 2048 + 256 + 2 * 64 * 4 + 64 + 1024;
+    HD_ENSURE_DYN_SMEM(conv_igemm_n64_kernel, smem_bytes);
+    alignas(64) CUtensorMap to;
+    uint64_t dims[4] = {(uint64_t)p.cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    uint64_t str[3] = {(uint64_t)p.out_cs * 2, (uint64_t)p.W * p.out_cs * 2, (uint64_t)p.H * p.W * p.out_cs * 2};
+    uint32_t box[4] = {32, 16, 2, 1};
+    int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle_bytes=*/64);
+    if (rc) return rc;
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_n64_kernel, grid, kN64Threads, smem_bytes, stream,
+                                     tx, tw, tx2, tw2, to, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -683,7 +950,8 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
                          const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
-                         cudaStream_t stream, int vtaps = 0, int pad_top = 0);
+                         cudaStream_t stream, int vtaps = 0, int pad_top = 0, const void* x2 = nullptr,
+                         const void* w2_packed = nullptr, int cin2 = 0);
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
@@ -713,6 +981,13 @@ extern "C" int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void*
                          out_cs, 0, 0, 1, nullptr, scale, shift, relu, stream);
 }
 
+extern "C" int hd_conv2d_igemm_dual(const void* x, const void* w_packed, const void* x2, const void* w2_packed, void* out,
+                                    const void* addend, int N, int H, int W, int cin, int cin2, int cout, int block_n,
+                                    int ksize, int out_cs, cudaStream_t stream) {
+    return conv_dispatch(x, w_packed, out, nullptr, nullptr, addend, nullptr, nullptr, N, H, W, cin, cout, block_n, ksize, 0,
+                         out_cs, 0, 0, 1, nullptr, nullptr, nullptr, 0, stream, 0, 0, x2, w2_packed, cin2);
+}
+
 extern "C" int hd_conv2d_igemm_vtaps(const void* x, const void* w_packed, void* out, const float* bias, float* stat_sum,
                                      float* stat_sqsum, int N, int H, int W, int cin, int cout, int block_n, int vtaps,
                                      int pad_top, int out_cs, const hd_bn_fuse* bn, const float* scale,
@@ -727,7 +1002,7 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
                          const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
-                         cudaStream_t stream, int vtaps, int pad_top) {
+                         cudaStream_t stream, int vtaps, int pad_top, const void* x2, const void* w2_packed, int cin2) {
     using namespace hd;
     HD_REQUIRE(bn == nullptr || (stat_sum != nullptr && bn->out && bn->counter && bn->gamma && bn->beta),
                "conv_igemm: fused BN finalize needs statistics, gamma/beta, an output block and a ticket counter");
@@ -783,6 +1058,20 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
             p.num_tiles = ht;
         }
     }
+    // N=64 halo kernel: 64 output channels on a map with enough 16x16 tiles to fill the machine (the 256x256 level)
+    bool n64 = false;
+    if (block_n == 64 && cout == 64 && out_mode == 0 && out2 == nullptr && H >= 16 && W >= 16 && p.kh <= 4 &&
+        g_conv_variant != 1) {
+        const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
+        n64 = g_conv_variant == 2 || ht >= sm_count();
+        if (n64) {
+            tw = 16; th = 16 + p.kh - 1; tn = 1;
+            p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
+            p.num_tiles = ht;
+        }
+    }
+    HD_REQUIRE(x2 == nullptr || (n64 && w2_packed && cin2 >= 64 && cin2 % 64 == 0 && cin2 <= 256),
+               "conv_igemm: a fused second 1x1 input needs the 64-output-channel halo kernel (large map, cout 64)");
     alignas(64) CUtensorMap tmx, tmw;
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -797,6 +1086,23 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
         uint32_t box[3] = {64, (uint32_t)block_n, 1};
         int rc = make_tmap_bf16(&tmw, w_packed, 3, dims, str, box);
         if (rc) return rc;
+    }
+    if (n64) {
+        alignas(64) CUtensorMap tmx2 = tmx, tmw2 = tmw;
+        if (x2) {
+            p.x2_chunks = cin2 / 64;
+            uint64_t dims[4] = {(uint64_t)cin2, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+            uint64_t str[3] = {(uint64_t)cin2 * 2, (uint64_t)W * cin2 * 2, (uint64_t)H * W * cin2 * 2};
+            uint32_t box[4] = {64, 16, 16, 1};
+            int rc = make_tmap_bf16(&tmx2, x2, 4, dims, str, box);
+            if (rc) return rc;
+            uint64_t wdims[3] = {(uint64_t)cin2, (uint64_t)block_n, 1};
+            uint64_t wstr[2] = {(uint64_t)cin2 * 2, (uint64_t)block_n * cin2 * 2};
+            uint32_t wbox[3] = {64, (uint32_t)block_n, 1};
+            rc = make_tmap_bf16(&tmw2, w2_packed, 3, wdims, wstr, wbox);
+            if (rc) return rc;
+        }
+        return launch_conv_n64(tmx, tmw, tmx2, tmw2, p, stream);
     }
     if (halo) return launch_conv_halo(tmx, tmw, p, stream);
     if (block_n == 128) return launch_conv<128>(tmx, tmw, p, stream);

@@ -46,10 +46,10 @@ int fail(int code, const char* fmt, ...);
         }                                                                                                    \
     } while (0)
 
-// Encode a tiled bf16 tensor map with 128B swizzle and zero OOB fill.
+// Encode a tiled bf16 tensor map (shared-memory swizzle of 128 / 64 / 0 bytes) with zero OOB fill.
 // dims/strides are innermost-first; strides[0] is implied (2 bytes) and strides_bytes has rank-1 entries.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 int sm_count();
 void count_launch();   // bumps the kernel-launch counter read by hd_launch_count()

@@ -244,6 +244,7 @@ extern "C" void hd_net_set_static_weights(hd_net* n, int on) {
 extern "C" int hd_net_num_units(const hd_net* n) { return static_cast<int>(n->units.size()); }
 
 // ------------------------------------------------------------------------------------------------ helpers
+static inline int hd_sm_count() { return hd::sm_count(); }
 static inline int block_n_for(int cout) { return cout > 64 ? 128 : (cout > 16 ? 64 : 16); }
 static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
@@ -687,9 +688,19 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     if (r.us < 0) {
         dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
     } else {
-        bf16* dXa = reinterpret_cast<bf16*>(n->bw.alloc(bytes_i));
-        dgrad_unit(n, r.u1, dY1, dXa, B, H, W, nullptr);
-        dgrad_unit(n, r.us, dYs, dX, B, H, W, dXa);
+        // dX = dgrad3x3(dY1) + dgrad1x1(dYs): one launch when the 64-output-channel halo kernel applies (the 256x256
+        // level, where this pair was 0.68 ms of the step), else two with the first result as the second's addend
+        Unit &u1 = n->units[r.u1], &us = n->units[r.us];
+        static const bool no_dual = getenv("HD_NO_DUAL_DGRAD") != nullptr;
+        const long long tiles16 = static_cast<long long>((W + 15) / 16) * ((H + 15) / 16) * B;
+        if (!no_dual && u1.cin == 64 && us.cin == 64 && H >= 16 && W >= 16 && tiles16 >= hd_sm_count()) {
+            RUN(hd_conv2d_igemm_dual(dY1, u1.wpd, dYs, us.wpd, dX, nullptr, B, H, W, pad64(u1.cout), pad64(us.cout), u1.cin,
+                                     64, 3, u1.cin, n->stream));
+        } else {
+            bf16* dXa = reinterpret_cast<bf16*>(n->bw.alloc(bytes_i));
+            dgrad_unit(n, r.u1, dY1, dXa, B, H, W, nullptr);
+            dgrad_unit(n, r.us, dYs, dX, B, H, W, dXa);
+        }
     }
     cudaEvent_t e1 = mark_ready(n);
     wgrad_unit(n, r.u1, r.X, dY1, B, H, W, e1);         // overlaps the next block's BN backward

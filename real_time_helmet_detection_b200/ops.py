@@ -98,6 +98,19 @@ def conv2d_igemm_affine(x: torch.Tensor, w_packed: torch.Tensor, cout: int, ksiz
     return out
 
 
+def conv2d_igemm_dual(x: torch.Tensor, w_packed: torch.Tensor, x2: torch.Tensor, w2_packed: torch.Tensor, cout: int,
+                      ksize: int, addend: torch.Tensor | None = None) -> torch.Tensor:
+    """conv_{k x k}(x; w) + conv_{1x1}(x2; w2) (+ addend) in one pass (64 output channels, large maps): the fused
+    dgrad of a `Residual` with a skip convolution."""
+    _lib.require_cuda(x, "x")
+    n, h, w, cin = x.shape
+    out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    check(_lib.lib().hd_conv2d_igemm_dual(ptr(x), ptr(w_packed), ptr(x2), ptr(w2_packed), ptr(out), ptr(addend), n, h, w,
+                                          cin, x2.shape[3], cout, w_packed.shape[1], ksize, cout, stream()),
+          "conv2d_igemm_dual")
+    return out
+
+
 def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, cin_real: int, ksize: int, grad: torch.Tensor | None = None,
                  accumulate: bool = False, stem_perm: bool = False) -> torch.Tensor:
     """x: NHWC bf16 [N,H,W,cin], dy: NHWC bf16 [N,H,W,128] -> grad OIHW fp32 [128, cin_real, k, k]."""

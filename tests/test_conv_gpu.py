@@ -216,3 +216,67 @@ def test_bn_fold_all(cuda_device):
     for t, o, c in zip(ts, outs, chans):
         sc = t[0] * torch.rsqrt(t[3] + 1e-5)
         assert torch.allclose(o[:c], sc, rtol=1e-6, atol=1e-7) and torch.allclose(o[c:], t[1] - t[2] * sc, rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 64-output-channel halo kernel (conv_igemm_n64_kernel): the 256x256 level of PreLayer - forced here on small maps with
+# hd_set_conv_variant(2), incl. image sizes that are not multiples of the 16x16 tile (zero-filled loads, clipped stores,
+# masked statistics), bias / addend / BN-statistics epilogue, and the fused second 1x1 input (the skip-branch dgrad).
+@pytest.fixture
+def force_halo():
+    from real_time_helmet_detection_b200 import _lib
+    _lib.lib().hd_set_conv_variant(2)
+    yield
+    _lib.lib().hd_set_conv_variant(0)
+
+
+@pytest.mark.parametrize("N,H,W,cin,k", [(2, 32, 32, 128, 3), (1, 48, 40, 128, 3), (3, 16, 16, 64, 3), (2, 32, 48, 128, 1),
+                                         (1, 20, 28, 64, 3), (1, 256, 256, 128, 3)])
+def test_conv_n64_forward_and_stats(cuda_device, force_halo, N, H, W, cin, k):
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(77 + H + cin + k)
+    cout = 64
+    x = _bf16_round(torch.randn(N, cin, H, W, generator=g))
+    w = _bf16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    bias = torch.randn(cout, generator=g)
+    r = _bf16_round(torch.randn(N, cout, H, W, generator=g))
+    ref = F.conv2d(x, w, bias, padding=(k - 1) // 2)
+    xd = ops.to_nhwc(x.to(cuda_device))
+    wp = ops.pack_weight(w.to(cuda_device), mode=0)
+    assert wp.shape[1] == 64
+    stats = torch.zeros(2, cout, device=cuda_device)
+    y = ops.to_nchw(ops.conv2d_igemm(xd, wp, cout, k, bias=bias.to(cuda_device), stats=stats)).cpu()
+    scale = ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= 1e-2 * scale and _rel_l2(y, ref) <= 3e-3
+    s1, s2 = ref.sum(dim=(0, 2, 3)), (ref * ref).sum(dim=(0, 2, 3))
+    assert torch.allclose(stats[0].cpu(), s1, rtol=1e-3, atol=1e-3 * s2.sqrt().max().item())
+    assert torch.allclose(stats[1].cpu(), s2, rtol=1e-3)
+    # the generic kernel (variant 1) gives the same tensor up to the bf16 rounding of the output
+    from real_time_helmet_detection_b200 import _lib
+    _lib.lib().hd_set_conv_variant(1)
+    y1 = ops.to_nchw(ops.conv2d_igemm(xd, wp, cout, k, bias=bias.to(cuda_device))).cpu()
+    _lib.lib().hd_set_conv_variant(2)
+    assert _rel_l2(y, y1) <= 2e-3
+    # addend epilogue
+    ya = ops.to_nchw(ops.conv2d_igemm(xd, wp, cout, k, addend=ops.to_nhwc(r.to(cuda_device)))).cpu()
+    assert _rel_l2(ya, F.conv2d(x, w, None, padding=(k - 1) // 2) + r) <= 3e-3
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 32, 32), (1, 40, 24), (1, 256, 256)])
+def test_conv_n64_dual_input_is_fused_residual_dgrad(cuda_device, force_halo, N, H, W):
+    """dX = dgrad3x3(dY1; W1) + dgrad1x1(dYs; Ws) of `Residual(64, 128)` (hourglass.py:111-127) in one launch ==
+    torch's conv_transpose pair in fp32 on the same bf16 operands."""
+    from real_time_helmet_detection_b200 import ops
+    g = torch.Generator().manual_seed(5 + H)
+    dy1 = _bf16_round(torch.randn(N, 128, H, W, generator=g))
+    dys = _bf16_round(torch.randn(N, 128, H, W, generator=g))
+    w1 = _bf16_round(torch.randn(128, 64, 3, 3, generator=g) * 0.03)
+    ws = _bf16_round(torch.randn(128, 64, 1, 1, generator=g) * 0.1)
+    ref = (torch.nn.grad.conv2d_input((N, 64, H, W), w1, dy1, padding=1) +
+           torch.nn.grad.conv2d_input((N, 64, H, W), ws, dys, padding=0))
+    w1d = ops.pack_weight(w1.to(cuda_device), mode=1)
+    wsd = ops.pack_weight(ws.to(cuda_device), mode=1)
+    assert w1d.shape == (9, 64, 128) and wsd.shape == (1, 64, 128)
+    out = ops.to_nchw(ops.conv2d_igemm_dual(ops.to_nhwc(dy1.to(cuda_device)), w1d, ops.to_nhwc(dys.to(cuda_device)), wsd,
+                                            64, 3)).cpu()
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() and _rel_l2(out, ref) <= 3e-3

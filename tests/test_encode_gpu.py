@@ -95,8 +95,23 @@ def test_encode_targets_full_size_vs_oracle_and_edge_cases():
     # empty slots only
     z = encode_targets(torch.zeros(2, 4, 4, device="cuda"), torch.full((2, 4), -1, device="cuda", dtype=torch.int32), (128, 128))
     assert all(float(t.abs().sum()) == 0.0 for t in z)
-    with pytest.raises(RuntimeError, match="exceeds"):
-        encode_targets(torch.zeros(1, 200, 4, device="cuda"), torch.zeros(1, 200, device="cuda", dtype=torch.int32), (128, 128))
+    # a crowded image: more boxes than one shared-memory chunk (128) - like the reference's box2hm, no cap; list order
+    # decides which box owns a shared centre cell, across chunk boundaries too
+    rs = np.random.RandomState(7)
+    nb = 300
+    x0, y0 = rs.uniform(0, 440, nb), rs.uniform(0, 440, nb)
+    crowd = np.stack([x0, y0, x0 + rs.uniform(6, 60, nb), y0 + rs.uniform(6, 60, nb)], 1).astype(np.float32)
+    crowd[129] = crowd[3]                                  # same centre cell in chunk 0 and chunk 1: the later one wins
+    crowd[129, 2:] += 1.0
+    labs = rs.randint(0, 2, nb)
+    got = encode_targets(torch.from_numpy(crowd)[None].cuda(), torch.from_numpy(labs.astype(np.int32))[None].cuda(), (512, 512))
+    want = encode_boxes(crowd.tolist(), labs.tolist(), (512, 512))
+    for name, g_, w_ in zip(("heat", "off", "size", "mask"), got, want):
+        g_ = g_[0].cpu().numpy()
+        if name == "heat":
+            assert np.abs(g_ - w_).max() <= 6e-8, np.abs(g_ - w_).max()
+        else:
+            assert np.array_equal(g_, w_), name
 
 
 @pytest.mark.gpu

@@ -227,10 +227,15 @@ int hd_loss_backward(const float* hm, long long hm_bs, const float* off, long lo
 /* ------------------------------------------------------------------ decode (transform.py:73-110, evaluate.py:126-182) */
 
 size_t hd_decode_scratch_bytes(int B, int S, int C, int H, int W);
-/* Two launches for the whole batch: (1) grid-wide sigmoid (apply_sigmoid) + 3x3 peak test + candidate compaction,
- * (2) one CTA per image: per stack exact joint top-k + gather + boxes + threshold, then (do_nms) class-agnostic hard
- * NMS over the concatenated stacks. heat/off/wh: fp32 planes with batch/stack
- * strides. Outputs: boxes [B][S*topk][4] fp32, cls [B][S*topk] int64, scores [B][S*topk] fp32, count [B] int32. */
+/* Zero the candidate counters at the head of a scratch buffer. Needed ONCE per buffer: hd_decode_nms expects them zero
+ * on entry and leaves them zero on exit (its second kernel cleans up after itself), so steady-state calls need no memset. */
+int hd_decode_scratch_init(void* scratch, int B, int S, hd_stream_t stream);
+/* Two launches for the whole batch: (1) grid-wide sigmoid (apply_sigmoid) + 3x3 peak test + candidate compaction - with
+ * conf_th > 0 only elements whose logit can reach the threshold take the nine-sigmoid test -, (2) one CTA per image: per
+ * stack exact joint top-k + gather + boxes + threshold, then (do_nms) class-agnostic hard NMS over the concatenated
+ * stacks (IoU bit matrix with one thread per pair, serial sweep, parallel write-out). heat/off/wh: fp32 planes with
+ * batch/stack strides. scratch: hd_decode_scratch_bytes(), initialised once with hd_decode_scratch_init().
+ * Outputs: boxes [B][S*topk][4] fp32, cls [B][S*topk] int64, scores [B][S*topk] fp32, count [B] int32. */
 int hd_decode_nms(const float* heat, long long bs_heat, long long ss_heat, const float* off, long long bs_off,
                   long long ss_off, const float* wh, long long bs_wh, long long ss_wh, int B, int S, int C, int H,
                   int W, int topk, float scale_factor, float conf_th, float nms_th, int normalized,

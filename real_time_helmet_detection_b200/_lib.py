@@ -69,6 +69,7 @@ _SIGNATURES = {
     "hd_encode_targets": (I, [P, P, I, I, I, I, I, I, I, P, P, P, P, P, P]),
     "hd_normalize_u8": (I, [P, P, I, I, I, P, P, P]),
     "hd_decode_scratch_bytes": (c_size_t, [I, I, I, I, I]),
+    "hd_decode_scratch_init": (I, [P, I, I, P]),
     "hd_decode_nms": (I, [P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, I, I, I, F, F, F, I, I, I, P, P, P, P, P, P]),
 }
 

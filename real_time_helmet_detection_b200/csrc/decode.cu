@@ -19,6 +19,8 @@
 // (oracle/decode_ref.py) fixes too. Zero-score fillers (only kept when conf_th <= 0, as in the reference) are the
 // lowest flat indices that are not positive peaks. Box arithmetic uses __f*_rn intrinsics (no FMA contraction) so
 // coordinates are bit-identical to the reference. Heat-map values must be >= 0 (probabilities / GT heat-maps).
+#include <cmath>
+
 #include "hd_common.h"
 
 namespace hd {
@@ -32,6 +34,7 @@ struct DecodeArgs {
     long long bs_heat, ss_heat, bs_off, ss_off, bs_wh, ss_wh;   // batch / stack strides (elements)
     int B, S, C, H, W, K;
     float scale_factor, conf_th, nms_th;
+    float logit_th;                  // logit(conf_th) - margin (see decode_peaks_kernel); -inf when conf_th <= 0
     int normalized, apply_sigmoid, do_nms;
     // scratch (per image-stack pair p = b*S + s)
     int* cand_count;                 // [B*S]
@@ -68,7 +71,16 @@ __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
     const bool fill = !(a.conf_th > 0.f);
     bool take = false;
     float me = 0.f;
-    if (inside) {
+    // With a positive confidence threshold only elements with sigmoid(logit) >= conf_th can ever be emitted (the
+    // reference thresholds after top-k, and a threshold commutes with a sorted prefix), so everything else skips the
+    // nine sigmoids of the peak test: one compare against logit(conf_th) minus a margin far above the rounding of expf.
+    // (A typical map keeps ~50 of 32,768 elements.) The exact `sigmoid(me) >= conf_th` test still follows below.
+    bool maybe = inside;
+    if (inside && !fill) {
+        const float raw = pl[y * a.W + x];
+        maybe = a.apply_sigmoid ? raw >= a.logit_th : raw >= a.conf_th;
+    }
+    if (maybe) {
         me = pl[y * a.W + x];
         if (a.apply_sigmoid) me = dsigmoid(me);
         float m = me;
@@ -287,6 +299,9 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
         __syncthreads();
     }
 
+    // self-cleaning scratch: the candidate counters of this image are dead from here on; leaving them at zero spares the
+    // next call its memset launch (contract of hd_decode_nms: counters zero on entry, zero on exit)
+    if (tid < a.S) a.cand_count[b * a.S + tid] = 0;
     // ------------------------------------------------------------------------------------------------ NMS
     const int N = ncand;
     float* ob = a.out_boxes + static_cast<size_t>(b) * a.S * K * 4;
@@ -312,49 +327,63 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
         order[tid] = tid;
     }
     __syncthreads();
-    // suppression bit matrix: bit j of row i set <=> j > i (in sorted order) and IoU(i, j) > nms_th
-    const int words = (N + 63) >> 6;
-    for (int t = tid; t < N * words; t += kSelThreads) {
-        const int i = t / words, wj = t - i * words;
-        const float* bi = cbox + 4 * order[i];
-        const float ax1 = bi[0], ay1 = bi[1], ax2 = bi[2], ay2 = bi[3];
-        const float aarea = __fmul_rn(__fsub_rn(ax2, ax1), __fsub_rn(ay2, ay1));
-        unsigned long long bits = 0ull;
-        const int j0 = wj << 6;
-        for (int jj = 0; jj < 64; ++jj) {
-            const int j = j0 + jj;
-            if (j <= i || j >= N) continue;
-            const float* bj = cbox + 4 * order[j];
-            const float w = fmaxf(0.f, __fsub_rn(fminf(ax2, bj[2]), fmaxf(ax1, bj[0])));
-            const float h = fmaxf(0.f, __fsub_rn(fminf(ay2, bj[3]), fmaxf(ay1, bj[1])));
-            const float inter = __fmul_rn(w, h);
-            const float barea = __fmul_rn(__fsub_rn(bj[2], bj[0]), __fsub_rn(bj[3], bj[1]));
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
-            if (iou > a.nms_th) bits |= 1ull << jj;
+    // suppression bit matrix: bit j of row i set <=> j > i (in sorted order) and IoU(i, j) > nms_th.
+    // One THREAD per (i, j) pair: a warp takes 32 consecutive j of one row and a ballot assembles the 32-bit word
+    // (N = 53 candidates: 106 warp tasks over 32 warps instead of 53 threads looping over 64 candidates each).
+    unsigned* mat32 = reinterpret_cast<unsigned*>(mat);                 // [N][jw]
+    const int jw = (N + 31) >> 5;
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int t = wid; t < N * jw; t += kSelThreads / 32) {
+            const int i = t / jw, w = t - i * jw;
+            const int j = (w << 5) + lane;
+            bool sup = false;
+            if (j > i && j < N) {
+                const float* bi = cbox + 4 * order[i];
+                const float* bj = cbox + 4 * order[j];
+                const float ax1 = bi[0], ay1 = bi[1], ax2 = bi[2], ay2 = bi[3];
+                const float aarea = __fmul_rn(__fsub_rn(ax2, ax1), __fsub_rn(ay2, ay1));
+                const float ww = fmaxf(0.f, __fsub_rn(fminf(ax2, bj[2]), fmaxf(ax1, bj[0])));
+                const float hh = fmaxf(0.f, __fsub_rn(fminf(ay2, bj[3]), fmaxf(ay1, bj[1])));
+                const float inter = __fmul_rn(ww, hh);
+                const float barea = __fmul_rn(__fsub_rn(bj[2], bj[0]), __fsub_rn(bj[3], bj[1]));
+                const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+                sup = iou > a.nms_th;
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0) mat32[t] = bits;
         }
-        mat[t] = bits;
     }
     __syncthreads();
-    // serial sweep by warp 0: lane l owns removed-word l
+    // serial sweep by warp 0 (lane l owns removed-word l; N <= 1024 = 32 words): it only records WHICH candidates
+    // survive - the next row's word is fetched before the current one is needed, and nothing is written to global
+    // memory inside the dependent chain. All threads then write the kept boxes in parallel.
+    int* kept = reinterpret_cast<int*>(keys);                           // [N] candidate indices in output order
     if (tid < 32) {
-        unsigned long long removed = 0ull;
+        unsigned removed = 0u;
         int nk = 0;
+        unsigned next = (N > 0 && tid < jw) ? mat32[tid] : 0u;
         for (int i = 0; i < N; ++i) {
-            const unsigned long long rw = __shfl_sync(0xffffffffu, removed, i >> 6);
-            if (!((rw >> (i & 63)) & 1ull)) {
-                if (tid == 0) {
-                    const int src = order[i];
-                    ob[4 * nk] = cbox[4 * src]; ob[4 * nk + 1] = cbox[4 * src + 1];
-                    ob[4 * nk + 2] = cbox[4 * src + 2]; ob[4 * nk + 3] = cbox[4 * src + 3];
-                    oc[nk] = ccls[src];
-                    os[nk] = cscore[src];
-                }
+            const unsigned row = next;
+            if (i + 1 < N && tid < jw) next = mat32[(i + 1) * jw + tid];
+            const unsigned rw = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((rw >> (i & 31)) & 1u)) {
+                if (tid == 0) kept[nk] = order[i];
                 ++nk;
-                if (tid < words) removed |= mat[i * words + tid];
+                removed |= row;
             }
         }
-        if (tid == 0) a.out_count[b] = nk;
+        if (tid == 0) misc[3] = nk;
     }
+    __syncthreads();
+    const int nk = misc[3];
+    for (int k = tid; k < nk; k += kSelThreads) {
+        const int src = kept[k];
+        *reinterpret_cast<float4*>(ob + 4 * k) = *reinterpret_cast<const float4*>(cbox + 4 * src);
+        oc[k] = ccls[src];
+        os[k] = cscore[src];
+    }
+    if (tid == 0) a.out_count[b] = nk;
 }
 
 constexpr size_t kSelSmem = static_cast<size_t>(kMaxCand) * kNmsWords * 8 + 2 * 1024 * 8 +
@@ -369,6 +398,14 @@ extern "C" size_t hd_decode_scratch_bytes(int B, int S, int C, int H, int W) {
     using namespace hd;
     const size_t chw = static_cast<size_t>(C) * H * W, ps = static_cast<size_t>(B) * S;
     return align256(ps * sizeof(int)) + align256(ps * chw * 8) + align256(ps * chw) + 256;
+}
+
+// Zero the candidate counters at the head of a decode scratch buffer (needed once per buffer; see hd_decode_nms).
+extern "C" int hd_decode_scratch_init(void* scratch, int B, int S, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(scratch != nullptr && B > 0 && S > 0, "decode_scratch_init: bad argument");
+    HD_CHECK_CUDA(cudaMemsetAsync(scratch, 0, align256(static_cast<size_t>(B) * S * sizeof(int)), stream));
+    return HD_OK;
 }
 
 // See include/hd_b200.h.
@@ -401,7 +438,15 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     a.cand_keys = reinterpret_cast<unsigned long long*>(sp + align256(ps * sizeof(int)));
     a.is_pos = sp + align256(ps * sizeof(int)) + align256(ps * chw * 8);
     a.out_boxes = out_boxes; a.out_cls = out_cls; a.out_scores = out_scores; a.out_count = out_count;
-    HD_CHECK_CUDA(cudaMemsetAsync(a.cand_count, 0, ps * sizeof(int), stream));
+    a.logit_th = -INFINITY;
+    if (conf_th > 0.f && conf_th < 1.f) {
+        // logit(conf_th) in double, minus an absolute margin of 1e-3 (+ 1e-3 relative): sigmoid'(x) <= 1/4, so the
+        // float sigmoid of anything below that is below conf_th by >= ~1e-4 * conf_th (1-conf_th), i.e. by thousands of ulps
+        const double lt = log(static_cast<double>(conf_th) / (1.0 - static_cast<double>(conf_th)));
+        a.logit_th = static_cast<float>(lt - 1e-3 - 1e-3 * fabs(lt));
+    } else if (conf_th >= 1.f) {
+        a.logit_th = 8.f;           // sigmoid(x) rounds to 1.0f only for x > ~16.6; keep everything above 8
+    }
     dim3 grid((W + 31) / 32, (H + 7) / 8, static_cast<unsigned>(ps * C));
     HD_CHECK_CUDA(::hd::launch_k(decode_peaks_kernel, grid, dim3(32, 8), 0, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .transform import _decode_call
+from .transform import _decode_buffers, _decode_call, _decode_scratch
 
 
 class _Captured:
@@ -40,6 +40,7 @@ class Prediction(torch.nn.Module):
         self.normalized_coord = normalized_coord
         self.cuda_graph = cuda_graph
         self._graphs = {}
+        self._scratch = {}         # decode scratch per (device, B, S, C, H, W): initialised once, self-cleaning afterwards
 
     def _decode_device(self, batch_output):
         """Enqueue-only part of decode(): (boxes (B,S*k,4), classes (B,S*k) i64, scores (B,S*k), counts (B,) i32)."""
@@ -55,8 +56,13 @@ class Prediction(torch.nn.Module):
         hw = H * W
         heat, off, wh = out, out[:, :, C:], out[:, :, C + 2:]
         strides = ((S * O * hw, O * hw),) * 3
+        key = (out.device, B, S, C, H, W)
+        scratch = self._scratch.get(key)
+        if scratch is None:
+            scratch = self._scratch[key] = _decode_scratch(out.device, B, S, C, H, W)
+        bufs = _decode_buffers(out.device, B, S, C, H, W, self.topk, scratch=scratch)
         return _decode_call(heat, off, wh, strides, B, S, C, H, W, self.topk, self.scale_factor, self.conf_th,
-                            self.nms_th, self.normalized_coord, True, True)
+                            self.nms_th, self.normalized_coord, True, True, bufs=bufs)
 
     @staticmethod
     def _to_lists(boxes, clss, scores, counts):

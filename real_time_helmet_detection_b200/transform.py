@@ -16,11 +16,20 @@ from . import _lib
 from ._lib import ptr, stream, check
 
 
-def _decode_buffers(dev, B, S, C, H, W, topk):
+def _decode_scratch(dev, B, S, C, H, W):
+    """Scratch of the decode kernels with its candidate counters zeroed (needed once per buffer: every call leaves them
+    zero again, csrc/decode.cu)."""
+    scratch = torch.empty((_lib.lib().hd_decode_scratch_bytes(B, S, C, H, W),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().hd_decode_scratch_init(ptr(scratch), B, S, stream(dev)), "decode_scratch_init")
+    return scratch
+
+
+def _decode_buffers(dev, B, S, C, H, W, topk, scratch=None):
     n = S * topk
     return (torch.empty((B, n, 4), dtype=torch.float32, device=dev), torch.empty((B, n), dtype=torch.int64, device=dev),
             torch.empty((B, n), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
-            torch.empty((_lib.lib().hd_decode_scratch_bytes(B, S, C, H, W),), dtype=torch.uint8, device=dev))
+            scratch if scratch is not None else _decode_scratch(dev, B, S, C, H, W))
 
 
 def _decode_call(heat, off, wh, strides, B, S, C, H, W, topk, scale_factor, conf_th, nms_th, normalized,

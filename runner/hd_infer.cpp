@@ -157,6 +157,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_logits, logits_n * sizeof(float)));
     CK(cudaMalloc(&d_ws, ws_bytes));
     CK(cudaMalloc(&d_scratch, hd_decode_scratch_bytes(1, S, C, h, w)));
+    HD(hd_decode_scratch_init(d_scratch, 1, S, stream));       // once: hd_decode_nms leaves the counters zeroed
     CK(cudaMalloc(&d_boxes, static_cast<size_t>(n_out) * 4 * sizeof(float)));
     CK(cudaMalloc(&d_cls, static_cast<size_t>(n_out) * sizeof(long long)));
     CK(cudaMalloc(&d_scores, static_cast<size_t>(n_out) * sizeof(float)));

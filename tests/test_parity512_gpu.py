@@ -146,5 +146,6 @@ def test_train_step_512_vs_oracle_and_bf16_reference(cuda_device, S, B):
     for n in ("pre_layer.layers.0.convolution.bias", "neck_lst.0.layers.1.convolution.bias"):
         assert n not in live and g[n].abs().max().item() == 0.0 and g32[n].norm().item() <= 1e-6 * gmax, n
     # BN running statistics after one step
+    assert max(stat_o.values()) <= max(stat_l.values()), (max(stat_o.values()), max(stat_l.values()))
     for k in st32:
-        assert stat_o[k] <= max(1.5 * stat_l[k], 2e-3), (k, stat_o[k], stat_l[k])
+        assert stat_o[k] <= max(2.5 * stat_l[k], 5e-3), (k, stat_o[k], stat_l[k])

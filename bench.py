@@ -477,7 +477,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)                   # NCCL prints its version banner to stdout at any debug level: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     S, size, B = args.num_stack, args.imsize, args.batch
     peaks = load_peaks()

@@ -400,7 +400,7 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvP
     constexpr int smem_bytes = kStages * (kABytes + BLOCK_N * 128) + 1024 /*align*/ + 256 /*barriers*/ +
                                2 * BLOCK_N * 4 + 8 * 2048 /*store staging*/;
     HD_ENSURE_DYN_SMEM(conv_igemm_kernel<BLOCK_N>, smem_bytes);
-    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    int grid = p.num_tiles < sm_budget() ? p.num_tiles : sm_budget();
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_kernel<BLOCK_N>, grid,
                                      BLOCK_N >= 64 ? 384 : kThreads,
                                      smem_bytes, stream, tx, tw, p));
@@ -914,7 +914,7 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
     uint32_t box[4] = {32, 16, 2, 1};
     int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle_bytes=*/0);
     if (rc) return rc;
-    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    int grid = p.num_tiles < sm_budget() ? p.num_tiles : sm_budget();
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes,
                                      stream, tx, tw,
                                      to, p));
@@ -932,7 +932,7 @@ static int launch_conv_n64(const CUtensorMap& tx, const CUtensorMap& tw, const C
     uint32_t box[4] = {32, 16, 2, 1};
     int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle_bytes=*/64);
     if (rc) return rc;
-    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    int grid = p.num_tiles < sm_budget() ? p.num_tiles : sm_budget();
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_n64_kernel, grid, kN64Threads, smem_bytes, stream,
                                      tx, tw, tx2, tw2, to, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();

@@ -276,14 +276,18 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const Wgr
 
 }  // namespace hd
 
+static int wgrad_ksplit(int N, int H, int W, int ksize, int sms);
 extern "C" int hd_conv2d_wgrad_ksplit(int N, int H, int W, int ksize) {
+    return wgrad_ksplit(N, H, W, ksize, hd::sm_count());      // the upper bound the workspace is sized for
+}
+static int wgrad_ksplit(int N, int H, int W, int ksize, int sms) {
     using namespace hd;
     int tw = 1 << ilog2_ceil(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2_ceil(H); if (th > 128 / tw) th = 128 / tw;
     int tn = 128 / (tw * th);
     int tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th) * ((N + tn - 1) / tn);
     int groups = ksize == 3 ? 3 : 1;
-    int ks = sm_count() / groups;
+    int ks = sms / groups;
     if (ks < 1) ks = 1;
     if (ks > tiles) ks = tiles;
     return ks;
@@ -325,7 +329,7 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     p.tw_log2 = ilog2_ceil(tw); p.th_log2 = ilog2_ceil(th); p.tn_log2 = ilog2_ceil(tn);
     p.tiles_x = (W + tw - 1) / tw; p.tiles_y = (H + th - 1) / th;
     p.num_tiles = p.tiles_x * p.tiles_y * ((N + tn - 1) / tn);
-    p.ksplit = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
+    p.ksplit = wgrad_ksplit(N, H, W, ksize, sm_budget());
     p.ws = reinterpret_cast<float*>(workspace);
     const bool halo = ksize == 3 && tw == 16 && th == 8;   // the dy taps become row offsets of one 10-row X tile
 

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2
-// Block-wide exclusive scan of one int per thread (1024 threads).
+// Block-wide exclusive scan of one int per thread (blockDim.x = 32 * nwarps <= 1024 threads).
 __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = v;
@@ -132,7 +132,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
     if (lane == 31) warp_sums[w] = inc;
     __syncthreads();
     if (w == 0) {
-        int s = warp_sums[lane];
+        int s = lane < static_cast<int>(blockDim.x >> 5) ? warp_sums[lane] : 0;
         int si = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;        // 1024, or 256 when few candidates are expected (conf_th > 0, S * K <= 256)
     const int HW = a.H * a.W;
     const int CHW = a.C * HW;
     const int K = a.K;
@@ -189,14 +190,14 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
         const int n = min(a.cand_count[p], CHW);
         int nsel;
         if (n <= K) {
-            for (int i = tid; i < n; i += kSelThreads) keys[i] = ck[i];
+            for (int i = tid; i < n; i += NT) keys[i] = ck[i];
             nsel = n;
             if (fill && n < K) {
                 // zero-score fillers: the lowest flat indices that are not positive peaks, in ascending order
                 const unsigned char* isp = a.is_pos + static_cast<size_t>(p) * CHW;
                 const int need = K - n;
                 int taken = 0;
-                for (int base = 0; base < CHW && taken < need; base += kSelThreads) {
+                for (int base = 0; base < CHW && taken < need; base += NT) {
                     const int i = base + tid;
                     const int flag = (i < CHW) && !isp[i];
                     int tot;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
             for (; shift >= 0; shift -= 8) {
                 if (tid < 256) hist[tid] = 0;
                 __syncthreads();
-                for (int i = tid; i < n; i += kSelThreads) {
+                for (int i = tid; i < n; i += NT) {
                     const unsigned long long key = ck[i];
                     if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
                         atomicAdd(&hist[static_cast<unsigned>(key >> shift) & 255u], 1);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
             }
             if (tid == 0) misc[2] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += kSelThreads) {
+            for (int i = tid; i < n; i += NT) {
                 const unsigned long long key = ck[i];
                 if (key >= prefix) keys[atomicAdd(&misc[2], 1)] = key;
             }
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
     long long* oc = a.out_cls + static_cast<size_t>(b) * a.S * K;
     float* os = a.out_scores + static_cast<size_t>(b) * a.S * K;
     if (!a.do_nms) {
-        for (int i = tid; i < N; i += kSelThreads) {
+        for (int i = tid; i < N; i += NT) {
             ob[4 * i] = cbox[4 * i]; ob[4 * i + 1] = cbox[4 * i + 1];
             ob[4 * i + 2] = cbox[4 * i + 2]; ob[4 * i + 3] = cbox[4 * i + 3];
             oc[i] = ccls[i];
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
     const int jw = (N + 31) >> 5;
     {
         const int lane = tid & 31, wid = tid >> 5;
-        for (int t = wid; t < N * jw; t += kSelThreads / 32) {
+        for (int t = wid; t < N * jw; t += NT >> 5) {
             const int i = t / jw, w = t - i * jw;
             const int j = (w << 5) + lane;
             bool sup = false;
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
     }
     __syncthreads();
     const int nk = misc[3];
-    for (int k = tid; k < nk; k += kSelThreads) {
+    for (int k = tid; k < nk; k += NT) {
         const int src = kept[k];
         *reinterpret_cast<float4*>(ob + 4 * k) = *reinterpret_cast<const float4*>(cbox + 4 * src);
         oc[k] = ccls[src];
@@ -451,7 +452,10 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     HD_CHECK_CUDA(::hd::launch_k(decode_peaks_kernel, grid, dim3(32, 8), 0, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     HD_ENSURE_DYN_SMEM(decode_select_nms_kernel, static_cast<int>(kSelSmem));
-    HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, kSelThreads, kSelSmem, stream, a));
+    // few candidates expected (positive threshold) and every per-candidate step fits 256 threads: a quarter of the warps
+    // makes the ~20 block-wide barriers of this latency-bound kernel that much cheaper
+    const int sel_threads = (conf_th > 0.f && static_cast<long long>(S) * topk <= 256) ? 256 : kSelThreads;
+    HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, sel_threads, kSelSmem, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -144,6 +144,13 @@ int sm_count() {
     return n;
 }
 
+static thread_local int t_sm_reserve = 0;
+int sm_reserve_set(int n) { int old = t_sm_reserve; t_sm_reserve = n < 0 ? 0 : n; return old; }
+int sm_budget() {
+    const int n = sm_count() - t_sm_reserve;
+    return n < 8 ? 8 : n;
+}
+
 }  // namespace hd
 
 extern "C" const char* hd_last_error(void) { return hd::err_buf(); }

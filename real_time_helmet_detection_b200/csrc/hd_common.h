@@ -52,6 +52,18 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 int sm_count();
+// SMs the persistent tensor-core kernels may fill: sm_count() minus the calling thread's reservation (SmReserve).
+// Inside the hourglass the executor runs two lanes (the `up1` branch beside the spine); a persistent conv / wgrad grid
+// of one CTA per SM owns every SM for its whole duration (all registers, ~200 KB of shared memory), so the other lane's
+// kernels - the latency-bound chain of the deep levels, 16-64 CTAs each - cannot start until it ends and the lanes
+// serialise at kernel granularity. Leaving a few SMs free lets that chain run underneath the big kernels.
+int sm_budget();
+int sm_reserve_set(int n);
+struct SmReserve {
+    int old;
+    explicit SmReserve(int n) : old(sm_reserve_set(n)) {}
+    ~SmReserve() { sm_reserve_set(old); }
+};
 void count_launch();   // bumps the kernel-launch counter read by hd_launch_count()
 bool pdl_enabled();    // programmatic dependent launch on (default) / off (hd_set_pdl(0) or HD_NO_PDL=1)
 bool pdl_allowed(unsigned grid_blocks);   // ... for a launch of this many CTAs under the calling thread's PdlScope

@@ -168,6 +168,12 @@ static bool stem_s2d() {
     return !im2col;
 }
 
+// SMs left free by the persistent conv / wgrad kernels while the hourglass runs its two lanes (HD_SM_RESERVE, default 16)
+static int hg_sm_reserve() {
+    static const int r = getenv("HD_SM_RESERVE") ? atoi(getenv("HD_SM_RESERVE")) : 16;
+    return r;
+}
+
 static const hd_unit_ptrs kNullUnit{};
 static inline const hd_unit_ptrs& UP(const hd_net* n, int ui) { return n->up ? n->up[ui] : kNullUnit; }
 
@@ -574,7 +580,10 @@ static void forward_impl(hd_net* n, const float* x, float* logits, int B, int H,
     for (int i = 0; i < n->S; ++i) {
         hd_net::StackSaved& s = n->stacks[i];
         s.x_in = xcur;
-        s.hg_out = hourglass_fwd(n, s.hg_root, xcur, B, H4, W4, training);
+        {
+            SmReserve lanes(training ? hg_sm_reserve() : 0);      // two lanes inside: see hd_common.h
+            s.hg_out = hourglass_fwd(n, s.hg_root, xcur, B, H4, W4, training);
+        }
         phase_mark(n, "hourglass");
         Unit& un = n->units[s.u_neck];
         s.Yn = reinterpret_cast<bf16*>(n->fw.alloc(act_bytes(B, H4, W4, C)));
@@ -793,7 +802,10 @@ static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
         wgrad_unit(n, s.u_neck, s.hg_out, dYn, B, H4, W4, en);
         bf16* dXi = reinterpret_cast<bf16*>(n->bw.alloc(full4));
         phase_mark(n, "head+neck bwd");
-        hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);
+        {
+            SmReserve lanes(hg_sm_reserve());
+            hourglass_bwd(n, s.hg_root, dHg, dXi, merge ? dXn : nullptr, B);
+        }
         phase_mark(n, "hourglass bwd");
         dXn = dXi;
     }

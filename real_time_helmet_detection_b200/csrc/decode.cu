@@ -20,6 +20,7 @@
 // lowest flat indices that are not positive peaks. Box arithmetic uses __f*_rn intrinsics (no FMA contraction) so
 // coordinates are bit-identical to the reference. Heat-map values must be >= 0 (probabilities / GT heat-maps).
 #include <cmath>
+#include <cstdlib>
 
 #include "hd_common.h"
 
@@ -57,17 +58,12 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 1
-// grid = (ceil(W/32), ceil(H/8), B*S*C), block = (32, 8): one thread per heat-map element.
-__global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
-    pdl_prologue();
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int z = blockIdx.z;
-    const int c = z % a.C, p = z / a.C;          // p = b*S + s
+// Peak test of ONE heat-map element per lane + warp-aggregated append to the candidate list of (image, stack) p.
+// Must be called by all 32 lanes of a warp with the same p (`inside` false for padding lanes).
+__device__ __forceinline__ void peak_test_append(const DecodeArgs& a, int p, int c, int y, int x, bool inside) {
     const int b = p / a.S, s = p - b * a.S;
     const int HW = a.H * a.W;
     const float* pl = a.heat + b * a.bs_heat + s * a.ss_heat + static_cast<long long>(c) * HW;
-    const bool inside = x < a.W && y < a.H;
     const bool fill = !(a.conf_th > 0.f);
     bool take = false;
     float me = 0.f;
@@ -102,7 +98,7 @@ __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
         take = pos_peak && (fill || me >= a.conf_th);
     }
     // warp-aggregated append
-    const unsigned lane = threadIdx.x;   // blockDim.x == 32: one warp per row of the block
+    const unsigned lane = threadIdx.x & 31u;
     const unsigned vote = __ballot_sync(0xffffffffu, take);
     if (vote) {
         int base = 0;
@@ -116,6 +112,16 @@ __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
                 (static_cast<unsigned long long>(fkey(me)) << 32) | (0xFFFFFFFFu - idx);
         }
     }
+}
+
+// grid = (ceil(W/32), ceil(H/8), B*S*C), block = (32, 8): one thread per heat-map element.
+__global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
+    pdl_prologue();
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = blockIdx.z;
+    const int c = z % a.C, p = z / a.C;          // p = b*S + s
+    peak_test_append(a, p, c, y, x, x < a.W && y < a.H);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2
@@ -159,9 +165,8 @@ __device__ __forceinline__ void rank_sort_desc(const unsigned long long* src, un
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const DecodeArgs a) {
-    pdl_prologue();
-    extern __shared__ __align__(16) unsigned char dsm[];
+// Per-image part: per stack top-k / gather / boxes / threshold, then NMS over the concatenated stacks. One CTA.
+__device__ __forceinline__ void select_nms_image(const DecodeArgs& a, const int b, unsigned char* dsm) {
     unsigned long long* mat = reinterpret_cast<unsigned long long*>(dsm);             // [kMaxCand][kNmsWords] 128 KB
     unsigned long long* keys = mat + kMaxCand * kNmsWords;                              // [1024] selected
     unsigned long long* sorted = keys + 1024;                                           // [1024]
@@ -173,9 +178,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
     int* wsum = hist + 256;          // 33 (+pad)
     int* misc = wsum + 40;
 
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int NT = blockDim.x;        // 1024, or 256 when few candidates are expected (conf_th > 0, S * K <= 256)
+    const int NT = blockDim.x;        // 1024 (256 is possible when S * K <= 256: measured no faster)
     const int HW = a.H * a.W;
     const int CHW = a.C * HW;
     const int K = a.K;
@@ -387,6 +391,50 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
     if (tid == 0) a.out_count[b] = nk;
 }
 
+__global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const DecodeArgs a) {
+    pdl_prologue();
+    extern __shared__ __align__(16) unsigned char dsm[];
+    select_nms_image(a, blockIdx.x, dsm);
+}
+
+// ------------------------------------------------------------------------------------------------ fused single launch
+// One thread-block CLUSTER per image does both steps: its kClusterSize CTAs scan disjoint slices of the image's
+// S * C * H * W logits (peak test + candidate append, as kernel 1), a cluster barrier (release / acquire at cluster scope:
+// the appended keys and counters are visible to the whole cluster) ends the scan, and CTA 0 of the cluster carries on
+// with the select / NMS part. Compared with the two-launch path this drops one kernel boundary (~2.5 us of a ~15 us
+// decode at batch 1) - used for conf_th > 0, where the scan is one compare per element and a handful of peak tests.
+constexpr int kClusterSize = 4;
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads, 1)
+decode_fused_kernel(const DecodeArgs a) {
+    pdl_prologue();
+    extern __shared__ __align__(16) unsigned char dsm[];
+    unsigned rank, cid;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    const int b = static_cast<int>(cid);
+    const int HW = a.H * a.W;
+    const int per_stack = a.C * HW;
+    // every thread of the cluster takes elements e = rank * NT + tid, + cluster-wide stride; whole warps stay together
+    const int stride = kClusterSize * static_cast<int>(blockDim.x);
+    for (int s = 0; s < a.S; ++s) {
+        const int p = b * a.S + s;
+        for (int e0 = 0; e0 < per_stack; e0 += stride) {
+            const int e = e0 + static_cast<int>(rank * blockDim.x + threadIdx.x);
+            const bool inside = e < per_stack;
+            const int ee = inside ? e : 0;
+            const int c = ee / HW, r = ee - c * HW;
+            const int y = r / a.W, x = r - y * a.W;
+            peak_test_append(a, p, c, y, x, inside);
+        }
+    }
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rank != 0) return;
+    select_nms_image(a, b, dsm);
+}
+
 constexpr size_t kSelSmem = static_cast<size_t>(kMaxCand) * kNmsWords * 8 + 2 * 1024 * 8 +
                             kMaxCand * (16 + 4 + 4 + 4) + 256 * 4 + 40 * 4 + 64;
 
@@ -448,14 +496,19 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     } else if (conf_th >= 1.f) {
         a.logit_th = 8.f;           // sigmoid(x) rounds to 1.0f only for x > ~16.6; keep everything above 8
     }
+    static const bool two_launches = getenv("HD_DECODE_TWO_LAUNCHES") != nullptr;
+    if (conf_th > 0.f && !two_launches) {
+        // single launch: one cluster of kClusterSize CTAs per image (see decode_fused_kernel)
+        HD_ENSURE_DYN_SMEM(decode_fused_kernel, static_cast<int>(kSelSmem));
+        HD_CHECK_CUDA(::hd::launch_k(decode_fused_kernel, B * kClusterSize, kSelThreads, kSelSmem, stream, a));
+        HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+        return HD_OK;
+    }
     dim3 grid((W + 31) / 32, (H + 7) / 8, static_cast<unsigned>(ps * C));
     HD_CHECK_CUDA(::hd::launch_k(decode_peaks_kernel, grid, dim3(32, 8), 0, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     HD_ENSURE_DYN_SMEM(decode_select_nms_kernel, static_cast<int>(kSelSmem));
-    // few candidates expected (positive threshold) and every per-candidate step fits 256 threads: a quarter of the warps
-    // makes the ~20 block-wide barriers of this latency-bound kernel that much cheaper
-    const int sel_threads = (conf_th > 0.f && static_cast<long long>(S) * topk <= 256) ? 256 : kSelThreads;
-    HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, sel_threads, kSelSmem, stream, a));
+    HD_CHECK_CUDA(::hd::launch_k(decode_select_nms_kernel, B, kSelThreads, kSelSmem, stream, a));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

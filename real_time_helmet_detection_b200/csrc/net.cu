@@ -168,9 +168,11 @@ static bool stem_s2d() {
     return !im2col;
 }
 
-// SMs left free by the persistent conv / wgrad kernels while the hourglass runs its two lanes (HD_SM_RESERVE, default 16)
+// SMs left free by the persistent conv / wgrad kernels while the hourglass runs its two lanes (HD_SM_RESERVE). Measured
+// on the B200 (round 2, same box, config 2): 0 / 8 / 16 / 24 / 32 reserved SMs -> 12.39 / 12.50 / 12.49 / 12.49 / 12.42 ms
+// per step, i.e. no gain - the free SMs are taken by the big lane's own elementwise kernels - so the default is 0.
 static int hg_sm_reserve() {
-    static const int r = getenv("HD_SM_RESERVE") ? atoi(getenv("HD_SM_RESERVE")) : 16;
+    static const int r = getenv("HD_SM_RESERVE") ? atoi(getenv("HD_SM_RESERVE")) : 0;
     return r;
 }
 

@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(kSelThreads, 1) decode_select_nms_kernel(const
 // One thread-block CLUSTER per image does both steps: its kClusterSize CTAs scan disjoint slices of the image's
 // S * C * H * W logits (peak test + candidate append, as kernel 1), a cluster barrier (release / acquire at cluster scope:
 // the appended keys and counters are visible to the whole cluster) ends the scan, and CTA 0 of the cluster carries on
-// with the select / NMS part. Compared with the two-launch path this drops one kernel boundary (~2.5 us of a ~15 us
-// decode at batch 1) - used for conf_th > 0, where the scan is one compare per element and a handful of peak tests.
+// with the select / NMS part. Compared with the two-launch path this drops one kernel boundary, but see hd_decode_nms:
+// measured 25 us vs 13 us at batch 1, so it is opt-in (HD_DECODE_FUSED=1) and the two launches stay the default.
 constexpr int kClusterSize = 4;
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads, 1)
@@ -496,9 +496,11 @@ extern "C" int hd_decode_nms(const float* heat, long long bs_heat, long long ss_
     } else if (conf_th >= 1.f) {
         a.logit_th = 8.f;           // sigmoid(x) rounds to 1.0f only for x > ~16.6; keep everything above 8
     }
-    static const bool two_launches = getenv("HD_DECODE_TWO_LAUNCHES") != nullptr;
-    if (conf_th > 0.f && !two_launches) {
-        // single launch: one cluster of kClusterSize CTAs per image (see decode_fused_kernel)
+    // Single launch (one 4-CTA cluster per image, decode_fused_kernel): built and tested, but MEASURED SLOWER on the B200
+    // at batch 1 - 25.2 us vs 12.9 us for the two launches below on the same box (round 2): the grid-wide first kernel
+    // scans with 128 CTAs, the cluster has 4, and the kernel boundary it saves costs less than that. Opt-in only.
+    static const bool fused = getenv("HD_DECODE_FUSED") != nullptr;
+    if (conf_th > 0.f && fused) {
         HD_ENSURE_DYN_SMEM(decode_fused_kernel, static_cast<int>(kSelSmem));
         HD_CHECK_CUDA(::hd::launch_k(decode_fused_kernel, B * kClusterSize, kSelThreads, kSelSmem, stream, a));
         HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();

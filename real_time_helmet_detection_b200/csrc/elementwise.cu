@@ -7,6 +7,8 @@
 // Per-channel BN statistics themselves are produced by the conv epilogue (conv_igemm.cu).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "hd_b200.h"
 #include "hd_common.h"
 
@@ -18,6 +20,19 @@ struct F8 {
 
 __device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    F8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ F8 cvt8(const uint4& u) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
     F8 r;
 #pragma unroll
@@ -295,8 +310,8 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ up1, const
 // streaming loop leaves it with no per-channel constants at all (mask from `out`) or just scale/shift (REMASK:
 // the ReLU mask of a plain conv+BN+ReLU is recomputed as y*scale+shift > 0, which saves reading the activated tensor),
 // so the kernel stays at ~50 registers and runs at HBM speed.
-template <bool SECOND, bool REMASK>
-__global__ void __launch_bounds__(256, SECOND ? 2 : 4)      // the two-BN variants need > 64 registers (they spilled at 4)
+template <bool SECOND, bool REMASK, bool U2 = false>
+__global__ void __launch_bounds__(256, SECOND ? 2 : (U2 ? 3 : 4))   // the two-BN variants need > 64 registers (they spilled at 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                      const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
@@ -324,8 +339,46 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     float a0[8], a1[8], a2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = a2[j] = 0.f;
-    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + row; pix < npix;
-         pix += static_cast<size_t>(gridDim.x) * rows) {
+    const size_t pstride = static_cast<size_t>(gridDim.x) * rows;
+    size_t pix = static_cast<size_t>(blockIdx.x) * rows + row;
+    if (!SECOND && U2) {
+        // Two pixels per iteration with all their 16-byte loads issued before the first use: beside a weight-gradient
+        // CTA only two of these CTAs fit on an SM (instead of eight), so the bytes in flight per THREAD decide the
+        // bandwidth this kernel gets in the concurrent windows of the backward pass.
+        for (; pix + pstride < npix; pix += 2 * pstride) {
+            const size_t o0 = pix * C + c0, o1 = (pix + pstride) * C + c0;
+            const uint4 rg0 = ldg16(dout + o0), ry0 = ldg16(y + o0);
+            const uint4 rg1 = ldg16(dout + o1), ry1 = ldg16(y + o1);
+            uint4 ro0 = make_uint4(0, 0, 0, 0), ro1 = ro0;
+            uint32_t m0 = 0, m1 = 0;
+            if (!REMASK) {
+                if (mbits) { m0 = mbits[o0 >> 3]; m1 = mbits[o1 >> 3]; }
+                else { ro0 = ldg16(out + o0); ro1 = ldg16(out + o1); }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const F8 g = cvt8(h ? rg1 : rg0), yy = cvt8(h ? ry1 : ry0);
+                F8 o;
+                if (!REMASK) {
+                    if (mbits) {
+                        const uint32_t m = h ? m1 : m0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o.v[j] = static_cast<float>((m >> j) & 1u);
+                    } else {
+                        o = cvt8(h ? ro1 : ro0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float pre = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) : o.v[j];
+                    const float gj = pre > 0.f ? g.v[j] : 0.f;
+                    a0[j] += gj;
+                    a1[j] = fmaf(gj, yy.v[j], a1[j]);
+                }
+            }
+        }
+    }
+    for (; pix < npix; pix += pstride) {
         const size_t off = pix * C + c0;
         F8 g = load8(dout + off);
         F8 yy = load8(y + off);
@@ -435,8 +488,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ s0, const float
 }
 
 // g = dout * (out > 0);  dy = a*g + b*y + c ; optionally dys = as*g + bs*ys + cs ; optionally gout = g
-template <bool SECOND, bool WRITE_G>
-__global__ void __launch_bounds__(256, SECOND ? 2 : 4) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+template <bool SECOND, bool WRITE_G, bool U2 = false>
+__global__ void __launch_bounds__(256, SECOND ? 2 : (U2 ? 3 : 4)) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                     const float* __restrict__ act_scale, const float* __restrict__ act_shift,
                                     const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
@@ -467,8 +520,49 @@ __global__ void __launch_bounds__(256, SECOND ? 2 : 4) bn_bwd_apply_kernel(const
     lds8(p[0], c0, ka);
     lds8(p[1], c0, kb);
     lds8(p[2], c0, kc);
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t istride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (!SECOND && U2) {          // two vectors per iteration, loads first (see bn_bwd_reduce_kernel)
+        float asc[8], ash[8];
+        if (remask) { lds8(p[6], c0, asc); lds8(p[7], c0, ash); }
+        for (; i + istride < nvec; i += 2 * istride) {
+            const size_t i1 = i + istride;
+            const uint4 rg0 = ldg16(dout + i * 8), ry0 = ldg16(y + i * 8);
+            const uint4 rg1 = ldg16(dout + i1 * 8), ry1 = ldg16(y + i1 * 8);
+            uint4 ro0 = make_uint4(0, 0, 0, 0), ro1 = ro0;
+            uint32_t m0 = 0, m1 = 0;
+            if (!remask) {
+                if (mbits) { m0 = mbits[i]; m1 = mbits[i1]; }
+                else { ro0 = ldg16(out + i * 8); ro1 = ldg16(out + i1 * 8); }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                F8 g = cvt8(h ? rg1 : rg0);
+                const F8 yy = cvt8(h ? ry1 : ry0);
+                F8 o, r;
+                if (remask) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] = fmaf(yy.v[j], asc[j], ash[j]);
+                } else if (mbits) {
+                    const uint32_t m = h ? m1 : m0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] = static_cast<float>((m >> j) & 1u);
+                } else {
+                    o = cvt8(h ? ro1 : ro0);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gj = o.v[j] > 0.f ? g.v[j] : 0.f;
+                    g.v[j] = gj;
+                    r.v[j] = fmaf(ka[j], gj, fmaf(kb[j], yy.v[j], kc[j]));
+                }
+                const size_t ii = h ? i1 : i;
+                store8(dy + ii * 8, r);
+                if (WRITE_G) store8(gout + ii * 8, g);
+            }
+        }
+    }
+    for (; i < nvec; i += istride) {
         F8 g = load8(dout + i * 8);
         F8 yy = load8(y + i * 8);
         F8 o, r, r2, y2;
@@ -754,7 +848,20 @@ static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const flo
     const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
-    if (mbits)
+    static const bool u2 = getenv("HD_BN_NO_UNROLL") == nullptr;      // two pixels per iteration (single-BN variants)
+    if (u2 && !ys && mbits)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false, true>, blocks, 256, smem, stream, BF(dout), nullptr,
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     mbits));
+    else if (u2 && !ys && out)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false, true>, blocks, 256, smem, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
+    else if (u2 && !ys)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true, true>, blocks, 256, smem, stream, BF(dout), nullptr,
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
+                                     static_cast<const uint8_t*>(nullptr)));
+    else if (mbits)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), nullptr,
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
                                      mbits));
@@ -820,7 +927,16 @@ static int bn_bwd_apply_impl(cvp dout, cvp out, const uint8_t* mbits, const floa
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     const int blocks = ew_blocks(nvec);
-    if (ys && gout)
+    static const bool u2 = getenv("HD_BN_NO_UNROLL") == nullptr;
+    if (u2 && !ys && gout)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, true, true>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr,
+                                     nullptr, nullptr, BFW(gout), nvec, C, mbits));
+    else if (u2 && !ys)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, false, true>, blocks, 256, 0, stream, BF(dout), BF(out),
+                                     act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr,
+                                     nullptr, nullptr, nullptr, nvec, C, mbits));
+    else if (ys && gout)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<true, true>, blocks, 256, 0, stream, BF(dout), BF(out),
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), BF(ys),
                                      coef_s, BFW(dys), BFW(gout), nvec, C, mbits));

@@ -98,6 +98,12 @@ void hd_set_conv_debug(int mode);
  * stem_perm: K index is the stem im2col order, grad_w is [cout][3][7][7] (hourglass.py:163). */
 int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W, int cin,
                     int cin_real, int cout, int ksize, int accumulate, int stem_perm, hd_stream_t stream);
+/* The same launch with caller-owned barrier words (two unsigned ints, ZERO on entry, left zero on exit) instead of the
+ * per-call memset of the workspace tail: the split-K partials are reduced INSIDE the kernel after a grid-wide barrier, so a
+ * sequence of weight-gradient launches on one stream needs neither a second kernel nor a memset in between. */
+int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W, int cin,
+                         int cin_real, int cout, int ksize, int accumulate, int stem_perm, unsigned int* sync_words,
+                         hd_stream_t stream);
 int hd_conv2d_wgrad_ksplit(int N, int H, int W, int ksize);
 size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, int ksize);
 

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "hd_set_conv_variant": (None, [I]),
     "hd_set_conv_debug": (None, [I]),
     "hd_conv2d_wgrad": (I, [P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "hd_conv2d_wgrad_sync": (I, [P, P, P, P, I, I, I, I, I, I, I, I, I, P, P]),
     "hd_conv2d_wgrad_ksplit": (I, [I, I, I, I]),
     "hd_conv2d_wgrad_workspace_bytes": (c_size_t, [I, I, I, I, I]),
     "hd_pack_all_weights": (I, [P, I, LL, P]),

@@ -11,8 +11,11 @@
 // Work split: grid = tap_groups x ksplit. A CTA owns one tap group (the three dx taps of one dy row for a
 // 3x3 kernel, or the single tap of a 1x1) and every ksplit-th 128-pixel tile; it keeps the group's
 // accumulators (3 x N fp32 columns) resident in TMEM over its whole pixel range, then writes one fp32
-// partial [tap][cout][cin] to the workspace. `hd_wgrad_reduce` sums the partials into the OIHW gradient.
+// partial [tap][cout][cin] to the workspace; after a grid-wide barrier every CTA sums its slice of the partials
+// into the OIHW gradient (no second launch).
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 
 #include "hd_common.h"
 #include "hd_ptx.cuh"
@@ -33,6 +36,11 @@ struct WgradParams {
     int tiles_x, tiles_y, num_tiles;
     float* ws;                 // [ksplit][taps][128][BLOCK_N]
     int taps;
+    // in-kernel split-K reduction (replaces the separate wgrad_reduce launch): after a grid-wide barrier on sync[0]
+    // every CTA sums its slice of the partials straight into the OIHW gradient
+    float* grad;
+    int cout, cin_real, accumulate, stem_perm;
+    unsigned int* sync;        // [2] zero on entry, zero on exit: arrivals | CTAs done reducing
 };
 
 // HALO (3x3 kernels on maps with a 16x8 pixel tile): a CTA owns the three dy taps of one dx COLUMN. The X operand of a
@@ -215,11 +223,73 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 __syncwarp();
             }
         }
+        __threadfence();       // this CTA's partials are visible device-wide before it announces itself below
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+
+    // ---- split-K reduction inside the kernel. The separate reduce launch (576 small CTAs) was the kernel the
+    // weight-gradient stream stalled on: whenever a persistent convolution of the main stream owns every SM (all
+    // registers) its CTAs cannot be placed at all - the trace showed the 12 us reduction taking 280-470 us at 256x256
+    // and delaying every weight gradient queued behind it. Here the grid (<= one CTA per SM, all co-resident once
+    // scheduled; nothing this kernel waits for depends on it) meets at a counter, then CTA b sums slice b of the
+    // partials (they are L2-resident: 29 MB per layer) in the fixed order k = 0..ksplit-1 - deterministic - into the
+    // OIHW gradient.
+    if (p.sync == nullptr) return;
+    const unsigned G = gridDim.x;
+    if (threadIdx.x == 0) {
+        atomicAdd(&p.sync[0], 1u);
+        unsigned spins = 0;
+        while (atomicAdd(&p.sync[0], 0u) < G) {
+            __nanosleep(64);
+            if (++spins > (1u << 25)) __trap();       // ~2 s: a lost CTA must surface as an error, not as a hang
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    {
+        const int total = p.taps * p.cout * p.cin_real;
+        const int chunk = (total + static_cast<int>(G) - 1) / static_cast<int>(G);
+        const int begin = static_cast<int>(blockIdx.x) * chunk;
+        const int end = begin + chunk < total ? begin + chunk : total;
+        const size_t stride = static_cast<size_t>(p.taps) * 128 * BLOCK_N;
+        for (int idx = begin + static_cast<int>(threadIdx.x); idx < end; idx += kWgThreads) {
+            const int ci = idx % p.cin_real;
+            const int co = (idx / p.cin_real) % p.cout;
+            const int tap = idx / (p.cin_real * p.cout);
+            const float* src = p.ws + (static_cast<size_t>(tap) * 128 + co) * BLOCK_N + ci;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int k = 0;
+            for (; k + 8 <= p.ksplit; k += 8) {
+                const float a0 = __ldcg(src + (k + 0) * stride), a1 = __ldcg(src + (k + 1) * stride);
+                const float a2 = __ldcg(src + (k + 2) * stride), a3 = __ldcg(src + (k + 3) * stride);
+                const float a4 = __ldcg(src + (k + 4) * stride), a5 = __ldcg(src + (k + 5) * stride);
+                const float a6 = __ldcg(src + (k + 6) * stride), a7 = __ldcg(src + (k + 7) * stride);
+                s0 += a0 + a4; s1 += a1 + a5; s2 += a2 + a6; s3 += a3 + a7;
+            }
+            for (; k < p.ksplit; ++k) s0 += __ldcg(src + k * stride);
+            const float sum = (s0 + s1) + (s2 + s3);
+            float* g = p.grad + (static_cast<size_t>(co) * p.cin_real + ci) * p.taps + tap;
+            if (p.stem_perm == 1) {
+                const int c = ci % 3, kk = ci / 3;   // kk = ky*7 + kx
+                g = p.grad + (static_cast<size_t>(co) * 3 + c) * 49 + kk;
+            } else if (p.stem_perm == 2) {           // space-to-depth stem (stem.cu): tap = dy, ci = dx*12 + (c*2+sy)*2 + sx
+                const int dx = ci / 12, q = ci % 12, c = q >> 2, sy = (q >> 1) & 1, sx = q & 1;
+                const int ky = 2 * tap + sy - 1, kx = 2 * dx + sx - 1;
+                if (ky < 0 || kx < 0) continue;      // the zero-weight taps of the 8x8 -> 7x7 embedding
+                g = p.grad + (static_cast<size_t>(co) * 3 + c) * 49 + ky * 7 + kx;
+            }
+            *g = p.accumulate ? (*g + sum) : sum;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&p.sync[1], 1u) == G - 1) {   // last CTA out: leave the words zeroed
+        p.sync[0] = 0u;
+        p.sync[1] = 0u;
+        __threadfence();
+    }
 }
 
 // grad[co][ci][tap] (+)= sum_s ws[s][tap][co][ci_pad]   (OIHW fp32, the layout of nn.Conv2d.weight.grad)
@@ -297,14 +367,34 @@ extern "C" size_t hd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int cin, 
     int ks = hd_conv2d_wgrad_ksplit(N, H, W, ksize);
     // at least 4 taps: the space-to-depth stem (stem_perm 2) runs as ksize 1 with four vertical taps
     const int taps = (ksize == 1 && cin == 64) ? 4 : ksize * ksize;
-    return static_cast<size_t>(ks) * taps * 128 * cin * sizeof(float);
+    return static_cast<size_t>(ks) * taps * 128 * cin * sizeof(float) + 256;      // + the two barrier words (see below)
 }
 
 // See include/hd_b200.h.
+extern "C" int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W,
+                                    int cin, int cin_real, int cout, int ksize, int accumulate, int stem_perm,
+                                    unsigned int* sync_words, cudaStream_t stream);
+
+// `workspace`: hd_conv2d_wgrad_workspace_bytes(); its last 256 bytes hold the kernel's two barrier words, zeroed here.
 extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W,
                                int cin, int cin_real, int cout, int ksize, int accumulate, int stem_perm,
                                cudaStream_t stream) {
     using namespace hd;
+    HD_REQUIRE(workspace != nullptr, "conv_wgrad: null workspace");
+    const size_t bytes = hd_conv2d_wgrad_workspace_bytes(N, H, W, cin, ksize);
+    unsigned int* sync = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + bytes - 256);
+    HD_CHECK_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), stream));
+    return hd_conv2d_wgrad_sync(x, dy, grad_w, workspace, N, H, W, cin, cin_real, cout, ksize, accumulate, stem_perm, sync,
+                                stream);
+}
+
+// Same with caller-owned barrier words: two unsigned ints that are ZERO on entry; the kernel leaves them zero again, so
+// a sequence of weight-gradient launches on one stream (the network's backward pass) needs no memset in between.
+extern "C" int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w, void* workspace, int N, int H, int W,
+                                    int cin, int cin_real, int cout, int ksize, int accumulate, int stem_perm,
+                                    unsigned int* sync_words, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(sync_words != nullptr, "conv_wgrad: null barrier words");
     // cout == 64: the second 64-channel atom of the dY tile is fetched out of bounds and zero-filled by TMA.
     HD_REQUIRE(cout == 128 || cout == 64, "conv_wgrad: cout=%d (tensor-core path needs 64 or 128)", cout);
     HD_REQUIRE(cin == 64 || cin == 128 || (cin == 192 && ksize == 1), "conv_wgrad: cin=%d unsupported", cin);
@@ -331,6 +421,10 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
     p.num_tiles = p.tiles_x * p.tiles_y * ((N + tn - 1) / tn);
     p.ksplit = wgrad_ksplit(N, H, W, ksize, sm_budget());
     p.ws = reinterpret_cast<float*>(workspace);
+    p.grad = grad_w; p.cout = cout; p.cin_real = cin_real; p.accumulate = accumulate; p.stem_perm = stem_perm;
+    // HD_WGRAD_SEPARATE_REDUCE=1: the round-1 scheme (partials + a second, separate reduction launch) for A/B timing
+    static const bool separate = getenv("HD_WGRAD_SEPARATE_REDUCE") != nullptr;
+    p.sync = separate ? nullptr : sync_words;
     const bool halo = ksize == 3 && tw == 16 && th == 8;   // the dy taps become row offsets of one 10-row X tile
 
     alignas(64) CUtensorMap tdy, tx;
@@ -352,9 +446,11 @@ extern "C" int hd_conv2d_wgrad(const void* x, const void* dy, float* grad_w, voi
              : (cin == 128) ? (halo ? launch_wgrad<128, true>(tdy, tx, p, stream) : launch_wgrad<128, false>(tdy, tx, p, stream))
                             : (halo ? launch_wgrad<64, true>(tdy, tx, p, stream) : launch_wgrad<64, false>(tdy, tx, p, stream));
     if (rc) return rc;
-    const int total = p.taps * cout * cin_real;
-    HD_CHECK_CUDA(::hd::launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, p.ws, grad_w, p.ksplit,
-                                 p.taps, cout, cin_real, 128, cin, accumulate, stem_perm));
-    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    if (p.sync == nullptr) {
+        const int total = p.taps * cout * cin_real;
+        HD_CHECK_CUDA(::hd::launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, p.ws, grad_w, p.ksplit,
+                                     p.taps, cout, cin_real, 128, cin, accumulate, stem_perm));
+        HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    }
     return HD_OK;
 }

@@ -106,6 +106,7 @@ struct hd_net {
     void* pack_jobs_dev = nullptr;          // device copy of the weight-pack job table
     void* fold_jobs_dev = nullptr;          // device copy of the eval-mode BN fold table
     unsigned int* tickets = nullptr;        // one zeroed word per unit: "last CTA finalizes the BN" ticket counters
+    unsigned int* wgrad_sync = nullptr;     // two zeroed words: grid barrier of the weight-gradient kernels
     // weight-gradient kernels run on a side stream so that they overlap the HBM-bound BN-backward kernels of the
     // main stream; their dY operands live in a bump-only region (`wg`) that is never reused within one backward pass
     Arena wg;
@@ -283,7 +284,10 @@ static void plan_persistent(hd_net* n) {
     n->alt.small = reinterpret_cast<float*>(a.alloc(16 * 256 * sizeof(float)));
     n->pack_jobs_dev = a.alloc(2 * n->units.size() * 64);
     n->fold_jobs_dev = a.alloc(n->units.size() * 64);
-    n->persist_bytes = (stats_total + n->units.size()) * sizeof(float);
+    // the per-forward memset also clears the first spare words behind the tickets: the two barrier words of the
+    // weight-gradient kernels' in-kernel split-K reduction (zero on entry, left zero by every launch)
+    n->wgrad_sync = n->tickets ? n->tickets + n->units.size() : nullptr;
+    n->persist_bytes = (stats_total + n->units.size() + 16) * sizeof(float);
 }
 
 // Host mirror of hd::PackJob (csrc/pack.cu).
@@ -624,11 +628,12 @@ static void wgrad_unit(hd_net* n, int ui, const bf16* x, const bf16* dy, int B, 
     const hd_unit_ptrs& p = UP(n, ui);
     wait_on(n, n->side, ready);
     if (u.kind == 1 && stem_s2d())
-        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 64, 48, 64, 1, 0, 2, n->side));
+        RUN(hd_conv2d_wgrad_sync(x, dy, p.dw, n->wgrad_ws, B, H, W, 64, 48, 64, 1, 0, 2, n->wgrad_sync, n->side));
     else if (u.kind == 1)
-        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->side));
+        RUN(hd_conv2d_wgrad_sync(x, dy, p.dw, n->wgrad_ws, B, H, W, 192, 147, 64, 1, 0, 1, n->wgrad_sync, n->side));
     else
-        RUN(hd_conv2d_wgrad(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->side));
+        RUN(hd_conv2d_wgrad_sync(x, dy, p.dw, n->wgrad_ws, B, H, W, pad64(u.cin), u.cin, u.cout, u.k, 0, 0, n->wgrad_sync,
+                                 n->side));
 }
 
 static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H, int W, const bf16* addend) {

@@ -422,9 +422,12 @@ extern "C" int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w
     p.ksplit = wgrad_ksplit(N, H, W, ksize, sm_budget());
     p.ws = reinterpret_cast<float*>(workspace);
     p.grad = grad_w; p.cout = cout; p.cin_real = cin_real; p.accumulate = accumulate; p.stem_perm = stem_perm;
-    // HD_WGRAD_SEPARATE_REDUCE=1: the round-1 scheme (partials + a second, separate reduction launch) for A/B timing
-    static const bool separate = getenv("HD_WGRAD_SEPARATE_REDUCE") != nullptr;
-    p.sync = separate ? nullptr : sync_words;
+    // Default: partials + a second, separate reduction launch. HD_WGRAD_FUSED_REDUCE=1 reduces inside the kernel behind
+    // the grid-wide barrier instead - built to stop the separate launch from starving behind persistent convolutions,
+    // but MEASURED SLOWER (round 2, same box: 12.46 / 12.54 vs 12.43 / 12.37 ms per step; 2 stacks 10.30 vs 10.17): CTAs
+    // spinning at the barrier hold their SMs, and 147 CTAs reduce more slowly than 576 small ones.
+    static const bool fused = getenv("HD_WGRAD_FUSED_REDUCE") != nullptr;
+    p.sync = fused ? sync_words : nullptr;
     const bool halo = ksize == 3 && tw == 16 && th == 8;   // the dy taps become row offsets of one 10-row X tile
 
     alignas(64) CUtensorMap tdy, tx;

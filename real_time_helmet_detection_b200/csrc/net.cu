@@ -710,6 +710,10 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
         static const bool no_dual = getenv("HD_NO_DUAL_DGRAD") != nullptr;
         const long long tiles16 = static_cast<long long>((W + 15) / 16) * ((H + 15) / 16) * B;
         if (!no_dual && u1.cin == 64 && us.cin == 64 && H >= 16 && W >= 16 && tiles16 >= hd_sm_count()) {
+            // this 0.45 ms persistent kernel owns every SM it runs on (all registers): leaving a few SMs out of its grid
+            // lets the weight-gradient stream's small kernels (the split-K reduction queued right now) get through
+            static const int n64_reserve = getenv("HD_N64_RESERVE") ? atoi(getenv("HD_N64_RESERVE")) : 0;
+            SmReserve room(n64_reserve);
             RUN(hd_conv2d_igemm_dual(dY1, u1.wpd, dYs, us.wpd, dX, nullptr, B, H, W, pad64(u1.cout), pad64(us.cout), u1.cin,
                                      64, 3, u1.cin, n->stream));
         } else {

@@ -12,6 +12,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0")
+torch.autograd.set_multithreading_enabled(False)    # backward on this thread, so that the NVTX range below covers it
 torch.manual_seed(777)
 net = StackedHourglass(S, 128, 6).to(dev).train()
 crit = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0)

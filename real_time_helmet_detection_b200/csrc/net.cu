@@ -99,6 +99,7 @@ struct hd_net {
     // `dX_pre` carries the gradient w.r.t. the PreLayer output across the stage boundary.
     bf16* dX_pre = nullptr;
     int bwd_stage = 0;                      // 0: no backward in flight, 1: stage 1 enqueued
+    bool comm_overlap = false;              // stage 1 handed a communication stream: a collective runs under stage 2
     cudaStream_t side_keep = nullptr;
     void* wgrad_ws = nullptr;
     size_t wgrad_ws_bytes = 0;
@@ -1039,12 +1040,21 @@ extern "C" int hd_net_backward_stage(hd_net* n, const hd_unit_ptrs* units, int n
         }
         if (n->rc != 0) { backward_end(n); return n->rc; }
         n->bwd_stage = 1;
+        n->comm_overlap = comm_stream != nullptr;
         return HD_OK;
     }
     HD_REQUIRE(n && n->bwd_stage == 1, "net_backward_stage: stage 2 without a pending stage 1");
     HD_REQUIRE(stream == n->stream && units == n->up, "net_backward_stage: stage 2 must use the stream / unit table of stage 1");
     n->rc = 0;
-    backward_impl(n, dlogits, 2);
+    {
+        // The collective of the stacks' bucket runs while this stage executes. Its kernel needs a few SMs; the persistent
+        // convolution / weight-gradient grids own every SM they run on, so without room the collective only advances
+        // between them (measured: overlap == no overlap at N = 8). HD_COMM_RESERVE leaves that many SMs out of their grids.
+        static const int comm_reserve = getenv("HD_COMM_RESERVE") ? atoi(getenv("HD_COMM_RESERVE")) : 0;
+        SmReserve room(n->comm_overlap ? comm_reserve : 0);
+        backward_impl(n, dlogits, 2);
+    }
+    n->comm_overlap = false;
     backward_end(n);
     return n->rc;
 }

@@ -75,7 +75,10 @@ def main():
                       f"   | max {col.max():7.3f}  min {col.min():7.3f}  mean {col.mean():7.3f}")
             sys.stdout.flush()
 
-    for mode in ("none", "flat", "flat+events", "overlap", "overlap+events"):
+    modes = os.environ.get("HD_TIMING_MODES", "none,flat,flat+events,overlap,overlap+events").split(",")
+    if rank == 0:
+        print("## env:", {k: v for k, v in os.environ.items() if k.startswith(("HD_", "NCCL_"))})
+    for mode in modes:
         run(mode)
     dist.barrier()
     dist.destroy_process_group()

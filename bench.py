@@ -665,8 +665,8 @@ def run_ours(args):
         if hook is not None:
             line["allreduce"] = {"collectives_per_step": hook.calls / max(1, hook.steps), "bytes_per_step": hook.elements * 4,
                                  "overlap": bool(hook.overlap), "op": "ncclAvg (no scaling kernel)",
-                                 "how": ("two buckets: stacks' gradients (82 % of the buffer) on a communication stream "
-                                         "under the PreLayer backward, PreLayer's gradients after the last wgrad"
+                                 "how": ("two buckets: everything but the 256x256 level (96 % of the buffer) on a communication stream "
+                                         "under that level's backward (8 SMs left free for the collective), the rest after the last wgrad"
                                          if hook.overlap else "one flat all-reduce after the backward pass")}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -755,10 +755,11 @@ static void hourglass_bwd(hd_net* n, int hi, const bf16* dOut, bf16* dX, const b
     n->bw.off = mark;
 }
 
-// stages: bit 0 = the stacks (head / neck / hourglass of every stack, last to first), bit 1 = PreLayer + stream join.
-// Every parameter gradient of the stacks - ~82 % of the flat gradient buffer for one stack, ~90 % for two - is complete
-// (on the side stream for the weights, on the caller's stream for BN / bias gradients) when stage 1 has been enqueued,
-// ~3 ms before the backward pass ends: that is where the data-parallel exchange of that bucket starts (parallel.py).
+// stages: bit 0 = the stacks (head / neck / hourglass of every stack, last to first) and the two 128x128 Residuals of
+// PreLayer, bit 1 = the 256x256 level of PreLayer (pool backward, Residual(64,128), stem) + stream join.
+// Every parameter gradient of stage 1 - 96 % of the flat gradient buffer for one stack - is complete (on the side stream
+// for the weights, on the caller's stream for BN / bias gradients) when stage 1 has been enqueued, ~3 ms before the
+// backward pass ends: that is where the data-parallel exchange of that bucket starts (parallel.py).
 static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
     const int B = n->B, C = n->in_ch;
     const int H2 = n->H / 2, W2 = n->W / 2, H4 = n->H / 4, W4 = n->W / 4;
@@ -821,16 +822,18 @@ static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
         phase_mark(n, "hourglass bwd");
         dXn = dXi;
     }
-    n->dX_pre = dXn;
-    }   // stage 1
-    if (!(stages & 2)) return;
-    dXn = n->dX_pre;
-    // PreLayer
+    // PreLayer, 128x128 part (the two Residuals behind the pool): still stage 1, so that the early gradient bucket covers
+    // everything but the 256x256 level (stem + Residual(64,128): 0.2 M of the 4.98 M parameters)
     bf16* dR3 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
     residual_bwd(n, n->r_pre4, dXn, dR3, B);
-    bf16* dP = reinterpret_cast<bf16*>(n->bw.alloc(full4));
-    residual_bwd(n, n->r_pre3, dR3, dP, B);
+    bf16* dP1 = reinterpret_cast<bf16*>(n->bw.alloc(full4));
+    residual_bwd(n, n->r_pre3, dR3, dP1, B);
     phase_mark(n, "pre4,3 bwd");
+    n->dX_pre = dP1;
+    }   // stage 1
+    if (!(stages & 2)) return;
+    bf16* dP = n->dX_pre;
+    // PreLayer, 256x256 part
     bf16* dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
     if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
     else RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
@@ -1050,7 +1053,8 @@ extern "C" int hd_net_backward_stage(hd_net* n, const hd_unit_ptrs* units, int n
         // The collective of the stacks' bucket runs while this stage executes. Its kernel needs a few SMs; the persistent
         // convolution / weight-gradient grids own every SM they run on, so without room the collective only advances
         // between them (measured: overlap == no overlap at N = 8). HD_COMM_RESERVE leaves that many SMs out of their grids.
-        static const int comm_reserve = getenv("HD_COMM_RESERVE") ? atoi(getenv("HD_COMM_RESERVE")) : 0;
+        // Measured at N = 8 (profiles/r02_allreduce_timing.txt): flat 13.89, overlap 13.76, overlap + 8 SMs 13.54, + 16 SMs 13.60 ms.
+        static const int comm_reserve = getenv("HD_COMM_RESERVE") ? atoi(getenv("HD_COMM_RESERVE")) : 8;
         SmReserve room(n->comm_overlap ? comm_reserve : 0);
         backward_impl(n, dlogits, 2);
     }

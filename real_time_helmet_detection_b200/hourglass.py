@@ -363,10 +363,10 @@ class StackedHourglass(nn.Module):
         sync = self.grad_sync
         with torch.cuda.device(d.device):
             if sync is not None and getattr(sync, "overlap", False) and sync.active():
-                # two buckets: the stacks' gradients (the tail of the flat buffer: parameters() lists pre_layer first)
-                # are exchanged on a communication stream while the PreLayer backward still runs; PreLayer's own
-                # gradients follow after the last weight-gradient kernel
-                n_pre = sum(p.numel() for p in self.pre_layer.parameters())
+                # two buckets: everything but the 256x256 level (the tail of the flat buffer: parameters() lists the stem
+                # and PreLayer's Residual(64,128) first) is exchanged on a communication stream while the 256x256 level's
+                # backward (~3 ms) still runs; those 0.2 M gradients follow after the last weight-gradient kernel
+                n_pre = sum(p.numel() for m in (self.pre_layer.layers[0], self.pre_layer.layers[1]) for p in m.parameters())
                 comm = sync.comm_stream(d.device)
                 args = (self._handle, tab, len(tab), ptr(d), ptr(self._workspace), self._workspace.numel(), stream(d.device))
                 check(L.hd_net_backward_stage(*args, 1, c_void_p(comm.cuda_stream)), "net_backward_stage(1)")

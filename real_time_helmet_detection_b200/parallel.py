@@ -5,10 +5,12 @@ bucket by bucket while autograd runs. Our whole backward pass is a single autogr
 gradient into one contiguous fp32 buffer (19.94 MB for 1 stack), so the exchange is at most TWO NCCL all-reduces over
 NVLink / NVSwitch on slices of that buffer:
 
-  * bucket "stacks" (hourglass + neck + head [+ merge] gradients, 82 % of the buffer for one stack) - enqueued on a
-    communication stream as soon as the stacks' backward has been enqueued (`hd_net_backward_stage`, csrc/net.cu), i.e.
-    it runs under the ~3 ms of PreLayer backward (the 256x256 level) that follow;
-  * bucket "pre_layer" (0.9 M parameters, 3.6 MB) - after the last weight-gradient kernel, on the compute stream.
+  * bucket "stacks" (hourglass + neck + head [+ merge] and the two 128x128 Residuals of PreLayer: 96 % of the buffer for
+    one stack) - enqueued on a communication stream as soon as that part of the backward has been enqueued
+    (`hd_net_backward_stage`, csrc/net.cu), i.e. it runs under the ~3 ms of the 256x256 level's backward that follow;
+    the persistent convolution grids of that stage leave 8 SMs free (HD_COMM_RESERVE) so the collective's CTAs can run
+    beside them instead of between them;
+  * bucket "pre_layer" (stem + Residual(64,128): 0.2 M parameters, 0.8 MB) - after the last weight-gradient kernel.
 
 Averaging (DDP semantics: sum / world) is done by NCCL itself (`ReduceOp.AVG`), so no scaling kernel follows.
 `overlap=False` restores the round-1 behaviour: one flat all-reduce after the whole backward pass. BatchNorm statistics

@@ -666,7 +666,7 @@ def run_ours(args):
             line["allreduce"] = {"collectives_per_step": hook.calls / max(1, hook.steps), "bytes_per_step": hook.elements * 4,
                                  "overlap": bool(hook.overlap), "op": "ncclAvg (no scaling kernel)",
                                  "how": ("two buckets: everything but the 256x256 level (96 % of the buffer) on a communication stream "
-                                         "under that level's backward (8 SMs left free for the collective), the rest after the last wgrad"
+                                         "under that level's backward, the rest after the last wgrad"
                                          if hook.overlap else "one flat all-reduce after the backward pass")}
         print(json.dumps(line), flush=True)
     if world > 1:

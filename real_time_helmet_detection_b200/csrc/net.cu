@@ -1053,8 +1053,10 @@ extern "C" int hd_net_backward_stage(hd_net* n, const hd_unit_ptrs* units, int n
         // The collective of the stacks' bucket runs while this stage executes. Its kernel needs a few SMs; the persistent
         // convolution / weight-gradient grids own every SM they run on, so without room the collective only advances
         // between them (measured: overlap == no overlap at N = 8). HD_COMM_RESERVE leaves that many SMs out of their grids.
-        // Measured at N = 8 (profiles/r02_allreduce_timing.txt): flat 13.89, overlap 13.76, overlap + 8 SMs 13.54, + 16 SMs 13.60 ms.
-        static const int comm_reserve = getenv("HD_COMM_RESERVE") ? atoi(getenv("HD_COMM_RESERVE")) : 8;
+        // Measured at N = 8 on two boxes (profiles/r02_allreduce_timing.txt): box A flat 13.89 / overlap 13.76 / + 8 SMs 13.54 /
+        // + 16 SMs 13.60 ms; box B (early bucket widened to 96 %) flat 13.63 / overlap 13.56 / + 8 SMs 13.75 - no robust
+        // gain from the reservation, so the default is 0.
+        static const int comm_reserve = getenv("HD_COMM_RESERVE") ? atoi(getenv("HD_COMM_RESERVE")) : 0;
         SmReserve room(n->comm_overlap ? comm_reserve : 0);
         backward_impl(n, dlogits, 2);
     }

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) decode_peaks_kernel(const DecodeArgs a) {
 
 // ------------------------------------------------------------------------------------------------ kernel 2
 // Block-wide exclusive scan of one int per thread (blockDim.x = 32 * nwarps <= 1024 threads).
-__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total, int nwarps) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
@@ -138,7 +138,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total
     if (lane == 31) warp_sums[w] = inc;
     __syncthreads();
     if (w == 0) {
-        int s = lane < static_cast<int>(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        int s = lane < nwarps ? warp_sums[lane] : 0;
         int si = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -179,12 +179,23 @@ __device__ __forceinline__ void select_nms_image(const DecodeArgs& a, const int 
     int* misc = wsum + 40;
 
     const int tid = threadIdx.x;
-    const int NT = blockDim.x;        // 1024 (256 is possible when S * K <= 256: measured no faster)
+    int NT = blockDim.x;              // 1024
     const int HW = a.H * a.W;
     const int CHW = a.C * HW;
     const int K = a.K;
     const bool fill = !(a.conf_th > 0.f);
     int ncand = 0;
+    // The common inference case - a positive threshold leaves a few dozen candidates - needs four warps, not thirty-two:
+    // every step below is per candidate, and the ~20 block-wide barriers of this latency-bound kernel cost ~0.3 us each
+    // with 32 warps. All threads read the (uniform) counts; warps 4.. leave before the first barrier.
+    if (!fill) {
+        int nmax = 0;
+        for (int s = 0; s < a.S; ++s) nmax = max(nmax, a.cand_count[b * a.S + s]);
+        if (nmax <= K && a.S * nmax <= 128) {
+            if (tid >= 128) return;
+            NT = 128;
+        }
+    }
 
     for (int s = 0; s < a.S; ++s) {
         const int p = b * a.S + s;
@@ -205,7 +216,7 @@ __device__ __forceinline__ void select_nms_image(const DecodeArgs& a, const int 
                     const int i = base + tid;
                     const int flag = (i < CHW) && !isp[i];
                     int tot;
-                    const int rank = taken + block_excl_scan(flag, wsum, &tot);
+                    const int rank = taken + block_excl_scan(flag, wsum, &tot, NT >> 5);
                     if (flag && rank < need)
                         keys[n + rank] = (static_cast<unsigned long long>(fkey(0.f)) << 32) |
                                          (0xFFFFFFFFu - static_cast<unsigned>(i));
@@ -299,7 +310,7 @@ __device__ __forceinline__ void select_nms_image(const DecodeArgs& a, const int 
             }
         }
         int nkeep;
-        block_excl_scan(keep, wsum, &nkeep);
+        block_excl_scan(keep, wsum, &nkeep, NT >> 5);
         ncand += nkeep;
         __syncthreads();
     }

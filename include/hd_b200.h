@@ -193,6 +193,13 @@ int hd_bn_bwd_reduce_fin_mask(const void* dout, const void* mask, const void* y,
                               const hd_bn_bwd_fuse* fin, hd_stream_t stream);
 int hd_bn_bwd_apply_mask(const void* dout, const void* mask, const void* y, const float* coef, void* dy, void* gout,
                          long long npix, int C, hd_stream_t stream);
+/* Reduce + coefficients + apply of ONE single-BN backward in one launch, for small maps (the latency-bound deep
+ * hourglass levels): a grid of <= 64 co-resident CTAs, the last one to arrive builds the coefficients and raises
+ * `epoch` (a device word the caller zero-initialises once; it only ever grows), all CTAs then apply them. mask: stored
+ * ReLU bits (then gout = dout * mask may be requested) or NULL (mask = y * act_scale + act_shift > 0). */
+int hd_bn_bwd_fused_small(const void* dout, const void* mask, const float* act_scale, const float* act_shift, const void* y,
+                          float* sums, void* dy, void* gout, long long npix, int C, const hd_bn_bwd_fuse* fin,
+                          unsigned int* epoch, hd_stream_t stream);
 int hd_bn_bwd_finalize(const float* s0, const float* s1, float count, const float* gamma, const float* mean,
                        const float* rstd, float* coef, float* dgamma, float* dbeta, int accumulate, int C,
                        hd_stream_t stream);

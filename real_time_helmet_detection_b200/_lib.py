@@ -57,6 +57,7 @@ _SIGNATURES = {
     "hd_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),
     "hd_bn_bwd_reduce_fin": (I, [P, P, P, P, P, P, P, P, P, LL, I, P, P]),
     "hd_bn_bwd_finalize": (I, [P, P, F, P, P, P, P, P, P, I, I, P]),
+    "hd_bn_bwd_fused_small": (I, [P, P, P, P, P, P, P, P, LL, I, P, P, P]),
     "hd_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, LL, I, P]),
     "hd_maxpool2_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "hd_bn_add_relu_pool2": (I, [P, P, P, P, P, P, P, P, I, I, I, I, P]),

@@ -299,10 +299,8 @@ __device__ __forceinline__ void select_nms_image(const DecodeArgs& a, const int 
                 ccls[ncand + tid] = cls;
             }
         }
-        int nkeep;
-        block_excl_scan(keep, wsum, &nkeep, NT >> 5);
-        ncand += nkeep;
-        __syncthreads();
+        // the kept entries are a prefix (scores are sorted), so only their count is needed: one barrier instead of a scan
+        ncand += __syncthreads_count(keep);
     }
 
     // self-cleaning scratch: the candidate counters of this image are dead from here on; leaving them at zero spares the

@@ -476,6 +476,137 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Reduce + finalize + apply of one single-BN backward in ONE launch, for the small maps of the deep hourglass levels
+// (<= 32x32 at batch 32: tensors of <= 8 MB that stay in L2). Those levels are latency-bound - a reduce launch (~15 us)
+// and an apply launch (~12 us) per BatchNorm regardless of size - and the two kernels differ only by a grid-wide
+// dependency: the coefficients. Here a grid of <= 64 CTAs (always co-resident: nothing this kernel waits for can be
+// waiting for it) accumulates the sums, the last CTA to arrive builds the coefficients and raises an epoch flag, every
+// CTA waits for it and applies them, re-reading its elements from L2.
+//   mask source: REMASK ? (y * act_scale + act_shift > 0) : stored bits (mbits).   WRITE_G: also emit g = dout * mask.
+template <bool REMASK, bool WRITE_G>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_fused_small_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ mbits,
+                          const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                          const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, __nv_bfloat16* __restrict__ dy,
+                          __nv_bfloat16* __restrict__ gout, size_t npix, int C, const hd_bn_bwd_fuse fin,
+                          unsigned int* __restrict__ epoch) {
+    pdl_prologue();
+    __shared__ __align__(16) float red[2 * 256];
+    __shared__ __align__(16) float kco[3][256];
+    __shared__ unsigned int s_e0;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_e0 = atomicAdd(epoch, 0u);          // read BEFORE this CTA's arrival below
+    const int cvec = C >> 3;
+    const int lane_c = threadIdx.x % cvec, row = threadIdx.x / cvec, rows = blockDim.x / cvec;
+    const int c0 = lane_c << 3;
+    float asc[8], ash[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        asc[j] = REMASK ? act_scale[c0 + j] : 0.f;
+        ash[j] = REMASK ? act_shift[c0 + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    const size_t pstride = static_cast<size_t>(gridDim.x) * rows;
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + row; pix < npix; pix += pstride) {
+        const size_t off = pix * C + c0;
+        const F8 g = load8(dout + off), yy = load8(y + off);
+        const uint32_t m = REMASK ? 0u : mbits[off >> 3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool on = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) > 0.f : ((m >> j) & 1u) != 0u;
+            const float gj = on ? g.v[j] : 0.f;
+            a0[j] += gj;
+            a1[j] = fmaf(gj, yy.v[j], a1[j]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (int o2 = cvec; o2 < 32; o2 <<= 1) {
+            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o2);
+            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o2);
+        }
+    }
+    if ((threadIdx.x & 31) < cvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&red[c0 + j], a0[j]);
+            atomicAdd(&red[C + c0 + j], a1[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(sums + c, red[c]);
+        atomicAdd(sums + C + c, red[C + c]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float S0 = __ldcg(sums + c);
+            const float g = fin.gamma[c], r = fin.rstd[c], m = fin.mean[c];
+            const float S1 = r * (__ldcg(sums + C + c) - m * S0);
+            fin.coef[c] = g * r;
+            fin.coef[C + c] = -g * r * r * S1 / fin.count;
+            fin.coef[2 * C + c] = g * r * (m * r * S1 - S0) / fin.count;
+            if (fin.dgamma) fin.dgamma[c] = S1;
+            if (fin.dbeta) fin.dbeta[c] = S0;
+            sums[c] = 0.f;
+            sums[C + c] = 0.f;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *fin.counter = 0u;
+            __threadfence();
+            atomicAdd(epoch, 1u);                   // release: the coefficients are complete
+        }
+    }
+    // every CTA (the last one included) waits for the epoch to move, then applies
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (atomicAdd(epoch, 0u) == s_e0) {
+            __nanosleep(32);
+            if (++spins > (1u << 25)) __trap();    // ~1 s: surface a lost CTA as an error instead of hanging
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        kco[0][c] = __ldcg(fin.coef + c);
+        kco[1][c] = __ldcg(fin.coef + C + c);
+        kco[2][c] = __ldcg(fin.coef + 2 * C + c);
+    }
+    __syncthreads();
+    float ka[8], kb[8], kc[8];
+    lds8(kco[0], c0, ka);
+    lds8(kco[1], c0, kb);
+    lds8(kco[2], c0, kc);
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + row; pix < npix; pix += pstride) {
+        const size_t off = pix * C + c0;
+        F8 g = load8(dout + off);
+        const F8 yy = load8(y + off);
+        const uint32_t m = REMASK ? 0u : mbits[off >> 3];
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool on = REMASK ? fmaf(yy.v[j], asc[j], ash[j]) > 0.f : ((m >> j) & 1u) != 0u;
+            const float gj = on ? g.v[j] : 0.f;
+            g.v[j] = gj;
+            r.v[j] = fmaf(ka[j], gj, fmaf(kb[j], yy.v[j], kc[j]));
+        }
+        store8(dy + off, r);
+        if (WRITE_G) store8(gout + off, g);
+    }
+}
+
 // From the reduction sums build the per-channel affine form of the BN input gradient
 //   dy = a * g + b * y + c      with  a = gamma*rstd, b = -gamma*rstd^2*S1/M, c = gamma*rstd*(mean*rstd*S1 - S0)/M
 // (S0 = sum g, S1 = sum g*yhat, recovered from the raw moment the reduce kernel accumulates)
@@ -895,6 +1026,35 @@ static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const flo
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr,
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
                                      static_cast<const uint8_t*>(nullptr)));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+// See include/hd_b200.h. One launch = reduce + coefficients + apply (single BN; mask bits or recomputed mask).
+extern "C" int hd_bn_bwd_fused_small(cvp dout, cvp mask, const float* act_scale, const float* act_shift, cvp y, float* sums,
+                                     void* dy, void* gout, long long npix, int C, const hd_bn_bwd_fuse* fin,
+                                     unsigned int* epoch, cudaStream_t stream) {
+    HD_REQUIRE(fin && fin->coef && fin->counter && fin->gamma && fin->mean && fin->rstd && fin->count > 0.f && epoch,
+               "bn_bwd_fused_small: incomplete finalize block");
+    HD_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "bn_bwd_fused_small: C=%d", C);
+    HD_REQUIRE(mask != nullptr || (act_scale && act_shift), "bn_bwd_fused_small: need mask bits or the activation scale/shift");
+    HD_REQUIRE(mask != nullptr || gout == nullptr, "bn_bwd_fused_small: the masked-gradient output goes with stored mask bits");
+    if (npix == 0) return HD_OK;
+    const int rows = 256 / (C / 8);
+    int blocks = static_cast<int>((npix + rows * 8 - 1) / (rows * 8));      // >= 8 pixels per thread-row and phase
+    if (blocks > 64) blocks = 64;                                            // co-residency of the whole grid
+    if (blocks < 1) blocks = 1;
+    const size_t np = static_cast<size_t>(npix);
+    const uint8_t* mb = reinterpret_cast<const uint8_t*>(mask);
+    if (mask && gout)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_fused_small_kernel<false, true>, blocks, 256, 0, stream, BF(dout), mb, act_scale,
+                                     act_shift, BF(y), sums, BFW(dy), BFW(gout), np, C, *fin, epoch));
+    else if (mask)
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_fused_small_kernel<false, false>, blocks, 256, 0, stream, BF(dout), mb, act_scale,
+                                     act_shift, BF(y), sums, BFW(dy), nullptr, np, C, *fin, epoch));
+    else
+        HD_CHECK_CUDA(::hd::launch_k(bn_bwd_fused_small_kernel<true, false>, blocks, 256, 0, stream, BF(dout), mb, act_scale,
+                                     act_shift, BF(y), sums, BFW(dy), nullptr, np, C, *fin, epoch));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

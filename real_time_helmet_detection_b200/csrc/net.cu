@@ -671,6 +671,14 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
     // instead of reading the stored block output (saves a 537 MB read per kernel at 256x256)
     const float* sc_s = s ? s->bnp : nullptr;
     const float* sh_s = s ? s->bnp + C : nullptr;
+    // small maps (the deep hourglass levels): one launch instead of two, see bn_bwd_fused_small_kernel
+    static const long long fused_max = getenv("HD_BN_FUSED_SMALL_MAX") ? atoll(getenv("HD_BN_FUSED_SMALL_MAX")) : 32768;
+    unsigned int* epoch = reinterpret_cast<unsigned int*>(n->small + 9 * 256) + 1;
+    if (!s && u.npix <= fused_max && (mask || out == nullptr)) {
+        RUN(hd_bn_bwd_fused_small(dout, mask, mask ? nullptr : u.bnp, mask ? nullptr : u.bnp + C, y, sums, dy,
+                                  mask ? gout : nullptr, u.npix, C, &fin, epoch, n->stream));
+        if (mask || gout == nullptr) return;
+    }
     if (mask && !s) {     // single-BN residual tail with stored ReLU mask bits: `out` is not read at all
         RUN(hd_bn_bwd_reduce_fin_mask(dout, mask, y, sums, u.npix, C, &fin, n->stream));
         RUN(hd_bn_bwd_apply_mask(dout, mask, y, coef, dy, gout, u.npix, C, n->stream));

@@ -302,3 +302,61 @@ def test_head_backward(cuda_device):
     close_bf16(nchw(dfeat), feat.grad, extra=1e-3 * feat.grad.abs().max().item())
     assert torch.allclose(dw.cpu(), w.grad.view(6, 128), rtol=1e-3, atol=1e-3 * w.grad.abs().max().item())
     assert torch.allclose(db.cpu(), b.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 16, 12), (32, 8, 8), (32, 32, 32), (1, 2, 2)])
+def test_bn_backward_fused_small(cuda_device, N, H, W):
+    """hd_bn_bwd_fused_small (reduce + coefficients + apply in ONE launch behind an epoch flag; the deep hourglass levels)
+    == the two-launch path, for both mask sources (stored bits with the masked gradient output, recomputed mask), and
+    back-to-back launches on the same scratch (sums / ticket / epoch are left ready for the next one)."""
+    import ctypes
+    from real_time_helmet_detection_b200 import ops, _lib
+
+    class Fuse(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_void_p) for k in ("gamma", "mean", "rstd", "coef", "dgamma", "dbeta", "gamma_s", "mean_s",
+                                                   "rstd_s", "coef_s", "dgamma_s", "dbeta_s")] + \
+                   [("count", ctypes.c_float), ("counter", ctypes.c_void_p)]
+
+    g = torch.Generator().manual_seed(80 + H)
+    d = cuda_device
+    C = 128
+    L = _lib.lib()
+    npix = N * H * W
+    y2, x = (nhwc(bf(torch.randn(N, C, H, W, generator=g)), d) for _ in range(2))
+    b2 = torch.stack([torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5, torch.randn(C, generator=g) * 0.1,
+                      torch.rand(C, generator=g) + 0.5]).to(d)                      # scale | shift | mean | rstd
+    out = torch.empty_like(y2)
+    mask = torch.zeros(npix * C // 8, dtype=torch.uint8, device=d)
+    _lib.check(L.hd_bn_add_relu_mask(_lib.ptr(y2), _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(x), None, None, _lib.ptr(out),
+                                     _lib.ptr(mask), npix, C, _lib.stream()))
+    dout = nhwc(bf(torch.randn(N, C, H, W, generator=g)), d)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(d)
+    scratch = torch.zeros(16 * 256, device=d)                    # sums [3][256] | coef [3][256] | ... | counter, epoch
+    sums, coef = scratch[:768], scratch[768:1536]
+    words = scratch[9 * 256:].view(torch.int32)
+    dgm, dbt = torch.empty(C, device=d), torch.empty(C, device=d)
+    fin = Fuse()
+    fin.gamma, fin.mean, fin.rstd = gamma.data_ptr(), b2[2].data_ptr(), b2[3].data_ptr()
+    fin.coef, fin.dgamma, fin.dbeta = coef.data_ptr(), dgm.data_ptr(), dbt.data_ptr()
+    fin.count, fin.counter = float(npix), words.data_ptr()
+    epoch = ctypes.c_void_p(words.data_ptr() + 4)
+    for rep in range(3):                                         # back-to-back on the same scratch
+        # (1) stored mask bits + masked gradient output: the Residual tail
+        ref = ops.bn_bwd(dout, out, y2, b2, gamma, want_g=True)
+        dy, gout = torch.empty_like(y2), torch.empty_like(y2)
+        _lib.check(L.hd_bn_bwd_fused_small(_lib.ptr(dout), _lib.ptr(mask), None, None, _lib.ptr(y2), _lib.ptr(sums),
+                                           _lib.ptr(dy), _lib.ptr(gout), npix, C, ctypes.byref(fin), epoch, _lib.stream()))
+        assert torch.equal(gout, ref[2])
+        assert (dy.float() - ref[0].float()).abs().max() <= 2 ** -7 * ref[0].float().abs().max() + 1e-6
+        assert torch.allclose(dgm, ref[3][0], rtol=1e-4, atol=1e-4) and torch.allclose(dbt, ref[3][1], rtol=1e-4, atol=1e-4)
+        # (2) mask recomputed from y * scale + shift: conv1's BN + ReLU
+        ref = ops.bn_bwd(dout, None, y2, b2, gamma, remask=True)
+        dy2 = torch.empty_like(y2)
+        _lib.check(L.hd_bn_bwd_fused_small(_lib.ptr(dout), None, _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(y2),
+                                           _lib.ptr(sums), _lib.ptr(dy2), None, npix, C, ctypes.byref(fin), epoch,
+                                           _lib.stream()))
+        assert (dy2.float() - ref[0].float()).abs().max() <= 2 ** -7 * ref[0].float().abs().max() + 1e-6
+        assert torch.allclose(dgm, ref[3][0], rtol=1e-4, atol=1e-4) and torch.allclose(dbt, ref[3][1], rtol=1e-4, atol=1e-4)
+    torch.cuda.synchronize()
+    assert int(words[0]) == 0 and int(words[1]) == 6             # ticket left at zero, six launches raised the epoch
+    assert float(sums.abs().max()) == 0.0                        # accumulators left zeroed

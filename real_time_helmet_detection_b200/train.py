@@ -57,10 +57,14 @@ def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, 
     image = image.to(device, non_blocking=True)
     gts = [t.to(device, non_blocking=True) for t in (gt_heatmap, gt_offset, gt_size, gt_mask)]   # once, not per stack
     outputs = network(image)                                   # (B, S, num_cls+4, H/4, W/4) fp32 logits
-    total_loss = 0
-    for s in range(outputs.shape[1]):
-        total_loss = total_loss + loss_calculator.forward_logits(outputs[:, s], *gts, num_cls=num_cls,
-                                                                 normalized_coord=normalized_coord)
+    S = outputs.shape[1]
+    total_loss = None
+    for s in range(S):
+        # one stack: a squeeze is a pure view in both directions; slicing would make autograd allocate a zero tensor of
+        # the full output and copy the slice's gradient into it (a fill + a copy on the critical path of every step)
+        logits_s = outputs.squeeze(1) if S == 1 else outputs[:, s]
+        loss_s = loss_calculator.forward_logits(logits_s, *gts, num_cls=num_cls, normalized_coord=normalized_coord)
+        total_loss = loss_s if total_loss is None else total_loss + loss_s
     do_step = step and optimizer is not None
     if scaler is not None:
         scaler.scale(total_loss).backward()

@@ -86,7 +86,8 @@ int hd_conv2d_igemm_affine(const void* x, const void* w_packed, void* out, const
 int hd_bn_fold_all(const void* jobs_host, int njobs, void* jobs_dev, hd_stream_t stream);
 
 /* Tuning / test knob for hd_conv2d_igemm: 0 = automatic choice (default), 1 = generic kernel only, 2 = use the
- * halo kernel (3x3, 128 output channels, map >= 16x16) whenever the shape is eligible. */
+ * halo kernel (3x3, 128 output channels, map >= 16x16) whenever the shape is eligible. Applies to the CALLING THREAD
+ * only (like hd_last_error). */
 void hd_set_conv_variant(int variant);
 /* Profiling only (results are wrong when non-zero): 1 = epilogue drains TMEM but skips math/stores, 2 = MMA issue
  * skipped (halo kernel). */

@@ -901,8 +901,9 @@ conv_igemm_n64_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
-static int g_conv_debug = 0;
-static int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible
+// test / tuning knobs: per calling thread, like the library's error state (no process-global mutable state)
+static thread_local int g_conv_debug = 0;
+static thread_local int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo whenever eligible
 
 static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 128 + 8 * 2048;

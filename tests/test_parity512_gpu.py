@@ -125,7 +125,7 @@ def test_train_step_512_vs_oracle_and_bf16_reference(cuda_device, S, B):
     assert rec["logits_rel_l2"]["ours"] <= 1.1 * rec["logits_rel_l2"]["lib_bf16"] + 1e-3, rec["logits_rel_l2"]
     assert rec["heatmap_logits_rel_l2"]["ours"] <= 1.1 * rec["heatmap_logits_rel_l2"]["lib_bf16"] + 1e-3
     # loss: 1e-3 of the fp32 value, or as close as the bf16 reference gets
-    assert abs(l - l32) <= max(1e-3 * abs(l32), 1.25 * abs(l16 - l32)), rec["loss"]
+    assert abs(l - l32) <= max(1e-3 * abs(l32), 1.5 * abs(l16 - l32)), rec["loss"]
     # every live parameter gradient (incl. the 256x256 level by name), per tensor and in aggregate
     assert len(live) >= len(names) - 4 * S and len(names) == (115 if S == 1 else 209)
     for n in live:

@@ -80,6 +80,69 @@ def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, 
     return total_loss.detach()
 
 
+class GraphedTrainStep:
+    """One training iteration (forward + fused loss + backward, train.py:97-134) recorded ONCE into a CUDA graph and
+    replayed: the ~260 kernel launches, ~100 cross-stream event edges and the autograd bookkeeping of a step become
+    one `cudaGraphLaunch`. Shapes are fixed by the example batch; every call copies the new batch into the graph's static
+    input tensors (host or device sources) and replays. Parameter gradients land in `p.grad` (static views of the flat
+    gradient buffer, rewritten by each replay), so an optimizer step between calls works as usual; BatchNorm running
+    statistics are updated by the replayed kernels exactly as in the eager step.
+
+    Single-GPU only (a NCCL exchange inside the backward node is not captured); the network must be in train() mode.
+    """
+
+    def __init__(self, network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, gt_mask, num_cls=2,
+                 normalized_coord=False, warmup=3):
+        if getattr(network, "grad_sync", None) is not None:
+            raise RuntimeError("GraphedTrainStep: a gradient exchange hook is attached; graphs are single-GPU only")
+        if not network.training:
+            raise RuntimeError("GraphedTrainStep records the training-mode step: call network.train() first")
+        self.network, self.loss_calculator = network, loss_calculator
+        self.num_cls, self.normalized_coord = num_cls, normalized_coord
+        device = next(network.parameters()).device
+        self.static_in = [t.to(device, copy=True) for t in (image, gt_heatmap, gt_offset, gt_size, gt_mask)]
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                  # eager warm-up: arena, streams, events, kernel attributes
+            for _ in range(warmup):
+                self._eager()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(device)
+        pending = list(loss_calculator._pending)       # the capture must not leave graph-pool tensors in the log queue
+        for p in network.parameters():
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager()
+            self.static_values = [v for v in loss_calculator._pending[len(pending):]]
+        loss_calculator._pending = pending
+
+    def _eager(self):
+        for p in self.network.parameters():
+            p.grad = None
+        outputs = self.network(self.static_in[0])
+        S = outputs.shape[1]
+        total = None
+        for s in range(S):
+            logits_s = outputs.squeeze(1) if S == 1 else outputs[:, s]
+            loss_s = self.loss_calculator.forward_logits(logits_s, *self.static_in[1:], num_cls=self.num_cls,
+                                                         normalized_coord=self.normalized_coord)
+            total = loss_s if total is None else total + loss_s
+        total.backward()
+        return total.detach()
+
+    def __call__(self, image, gt_heatmap, gt_offset, gt_size, gt_mask, log=True):
+        for dst, src in zip(self.static_in, (image, gt_heatmap, gt_offset, gt_size, gt_mask)):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        if log:                                        # LossCalculator.log keeps working: one small copy per stack
+            for v in self.static_values:
+                self.loss_calculator._record(v.clone())
+        return self.static_loss.clone()
+
+
 class DevicePrefetcher:
     """Iterates over host batches (tuples of pinned CPU tensors) and yields them on the device, copying batch i+1 on a
     side stream while batch i is being consumed — the H2D copy of every step still happens, it just overlaps compute.

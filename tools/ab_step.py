@@ -30,6 +30,14 @@ def step():
     return train_step(net, crit, x, *gts)
 
 
+if os.environ.get("AB_GRAPH"):                       # the same step replayed from a CUDA graph
+    from real_time_helmet_detection_b200.train import GraphedTrainStep
+    graphed = GraphedTrainStep(net, crit, x, *gts)
+
+    def step():                                       # noqa: F811
+        return graphed(x, *gts, log=False)
+
+
 for _ in range(6):
     step()
 torch.cuda.synchronize()
@@ -42,6 +50,6 @@ for rep in range(3):
     e1.record()
     torch.cuda.synchronize()
     best.append(e0.elapsed_time(e1) / steps)
-knobs = {k: v for k, v in os.environ.items() if k.startswith("HD_")}
+knobs = {k: v for k, v in os.environ.items() if k.startswith(("HD_", "AB_"))}
 print(f"ab_step B={B} S={S} {knobs}: ms/step {min(best):.3f} (reps {', '.join('%.3f' % b for b in best)})  "
       f"img/s {B / min(best) * 1e3:.1f}  loss {float(loss):.4f}", flush=True)

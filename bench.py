@@ -515,7 +515,10 @@ def run_ours(args):
         for p in net.parameters():
             p.grad = None
         batch = next(loader)                                    # this step's inputs, copied from pinned host memory
-        loss = train_step(net, crit, *batch)
+        if e2e_state.get("graphed") is not None:                # device batch -> the graph's static inputs (d2d) -> replay
+            loss = e2e_state["graphed"](*batch, log=False)
+        else:
+            loss = train_step(net, crit, *batch)
         loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
         loss_evt[i & 1].record()
         if i > 0:
@@ -549,12 +552,38 @@ def run_ours(args):
     warmup = max(3, args.warmup)
     for _ in range(warmup):
         step_device()
+    # Single GPU: the measured step is the same iteration replayed from a CUDA graph (train.GraphedTrainStep: one
+    # cudaGraphLaunch instead of ~260 kernel launches + ~100 cross-stream event edges; identical kernels and work). The
+    # eager step is timed as well and reported beside it. N > 1 stays eager (the NCCL exchange lives in the backward node).
+    graphed, graph_launches, eager = None, 0, None
+    if world == 1 and not args.no_graph:
+        try:
+            from real_time_helmet_detection_b200.train import GraphedTrainStep
+            l0 = _lib.lib().hd_launch_count()
+            graphed = GraphedTrainStep(net, crit, image_d, *gts_d, warmup=0)
+            graph_launches = _lib.lib().hd_launch_count() - l0          # kernels recorded into the graph = per replay
+        except Exception as exc:                                        # capture not possible: stay eager, say so
+            graphed, eager = None, {"graph_error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    if graphed is not None:
+        ms_eager, launches_eager, _, _ = timed(step_device, args.steps)
+        eager = {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": "img/s", "ms_per_step": ms_eager / args.steps,
+                 "gpu_launches": int(launches_eager), "what": "the same step launched kernel by kernel (no CUDA graph)"}
+
+        def step_measured():                             # inputs resident in HBM: the graph's own static tensors
+            return graphed(*graphed.static_in, log=False)
+        for _ in range(3):
+            step_measured()
+    else:
+        step_measured = step_device
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms, launches, t0, t1 = timed(step_device, args.steps)
+    ms, launches, t0, t1 = timed(step_measured, args.steps)
+    if graphed is not None:
+        launches = graph_launches * args.steps          # replayed kernels (hd_launch_count only sees the capture)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    e2e_state["graphed"] = graphed
     for _ in range(max(args.warmup, 5)):    # the prefetch stream's allocator blocks need a few steps to settle
         step_e2e()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
@@ -646,7 +675,8 @@ def run_ours(args):
                            "l2": "no explicit flush: ~10 GB of activations per step >> 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
-                        "how": "train.train_step on pinned host batches via train.DevicePrefetcher (H2D of step i+1 "
+                        "how": ("train.GraphedTrainStep" if graphed is not None else "train.train_step") +
+                               " on pinned host batches via train.DevicePrefetcher (H2D of step i+1 "
                                "overlaps step i); every step's loss is copied D2H and read on the host one step later"},
                 "e2e_device_collate": {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": "img/s",
                                        "h2d_bytes_per_step": collate.h2d_bytes * world, "ms_per_step": ms_u8 / args.steps,
@@ -656,6 +686,10 @@ def run_ours(args):
                                               "images is inside the timed region"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "decode": dec,
                 "inference_b1": infer}
+        line["config"]["launch"] = ("CUDA graph replay of the whole iteration (train.GraphedTrainStep)" if graphed is not None
+                                    else "eager (kernel by kernel)")
+        if eager is not None:
+            line["eager"] = eager
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if lib is not None:
@@ -686,6 +720,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: time the eager step only (no CUDA-graph replay)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one flat all-reduce after backward (round-1 behaviour)")
     args = ap.parse_args()
     if args.impl == "reference":

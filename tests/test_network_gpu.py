@@ -252,36 +252,44 @@ def test_ragged_shapes_train_and_eval(cuda_device, B, H, W):
 
 def test_graphed_train_step_matches_eager(cuda_device):
     """train.GraphedTrainStep: the whole iteration (three streams, ~260 launches, autograd) replayed from a CUDA graph
-    gives the eager step's loss, gradients and BN running statistics on new batches, and `LossCalculator.log` keeps working."""
+    gives the eager step's loss, gradients and BN running statistics on new batches, and `LossCalculator.log` keeps
+    working. Gradients of a batch-2 step carry run-to-run noise (fp32 atomics order feeding BN backward, SURVEY hard
+    parts): the bar is the distance between two EAGER replicas on the same inputs."""
     from real_time_helmet_detection_b200.hourglass import StackedHourglass
     from real_time_helmet_detection_b200.loss import LossCalculator
     from real_time_helmet_detection_b200.train import GraphedTrainStep, train_step
     torch.manual_seed(5)
-    net_a = StackedHourglass(1, 128, 6).to(cuda_device).train()
-    net_b = StackedHourglass(1, 128, 6).to(cuda_device).train()
-    net_b.load_state_dict(net_a.state_dict())
-    crit_a, crit_b = LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0), LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0)
-    gts = [g.to(cuda_device) for g in _gt(192, 2)]
+    nets = [StackedHourglass(1, 128, 6).to(cuda_device).train() for _ in range(3)]      # eager, eager, graphed
+    for n in nets[1:]:
+        n.load_state_dict(nets[0].state_dict())
+    crits = [LossCalculator(1.0, 1.0, 0.1, 2.0, 4.0) for _ in range(3)]
+    gts = [g.to(cuda_device) for g in _gt(192, 4)]
     gen = torch.Generator(cuda_device).manual_seed(3)
-    x0 = torch.randn(2, 3, 192, 192, device=cuda_device, generator=gen)
-    sd0 = {k: v.clone() for k, v in net_a.state_dict().items()}
-    graphed = GraphedTrainStep(net_b, crit_b, x0, *gts)
-    net_b.load_state_dict(sd0)                          # the warm-up / capture runs moved the BN running statistics
-    crit_b.log = {k: [] for k in ("hm", "offset", "size", "total")}
+    x0 = torch.randn(4, 3, 192, 192, device=cuda_device, generator=gen)
+    sd0 = {k: v.clone() for k, v in nets[0].state_dict().items()}
+    graphed = GraphedTrainStep(nets[2], crits[2], x0, *gts)
+    nets[2].load_state_dict(sd0)                        # the warm-up / capture runs moved the BN running statistics
+    crits[2].log = {k: [] for k in ("hm", "offset", "size", "total")}
+
+    def flat(net):
+        return torch.cat([p.grad.flatten() for p in net.parameters()])
+
     for i in range(3):
-        x = torch.randn(2, 3, 192, 192, device=cuda_device, generator=gen)
-        for p in net_a.parameters():
-            p.grad = None
-        la = train_step(net_a, crit_a, x, *gts)
-        lb = graphed(x, *gts)
-        assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(la)), (i, float(la), float(lb))
-        ga = torch.cat([p.grad.flatten() for p in net_a.parameters()])
-        gb = torch.cat([p.grad.flatten() for p in net_b.parameters()])
-        assert torch.isfinite(gb).all()
-        assert rel(gb, ga) <= 5e-2, rel(gb, ga)          # run-to-run atomics-order noise of the same kernels
-    for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+        x = torch.randn(4, 3, 192, 192, device=cuda_device, generator=gen)
+        losses = []
+        for n, c in zip(nets[:2], crits[:2]):
+            for p in n.parameters():
+                p.grad = None
+            losses.append(float(train_step(n, c, x, *gts)))
+        lg = float(graphed(x, *gts))
+        assert abs(lg - losses[0]) <= max(2e-3 * abs(losses[0]), 3 * abs(losses[1] - losses[0])), (i, lg, losses)
+        ga, gb, gg = flat(nets[0]), flat(nets[1]), flat(nets[2])
+        assert torch.isfinite(gg).all()
+        noise = rel(gb, ga)
+        assert rel(gg, ga) <= 3.0 * noise + 1e-2, (i, rel(gg, ga), noise)
+    for (k, a), (_, b) in zip(nets[0].state_dict().items(), nets[2].state_dict().items()):
         if "running" in k:
-            assert torch.allclose(a, b, rtol=1e-3, atol=1e-4), k
+            assert torch.allclose(a, b, rtol=2e-3, atol=2e-4), k
         if "num_batches_tracked" in k:
             assert int(a) == int(b) == 3, k
-    assert len(crit_b.log["total"]) == 3 and abs(crit_b.log["total"][-1] - float(lb)) < 1e-4
+    assert len(crits[2].log["total"]) == 3 and abs(crits[2].log["total"][-1] - lg) < 1e-4

@@ -512,12 +512,18 @@ def run_ours(args):
 
     def step_e2e():
         i = e2e_state["i"]
-        for p in net.parameters():
-            p.grad = None
-        batch = next(loader)                                    # this step's inputs, copied from pinned host memory
-        if e2e_state.get("graphed") is not None:                # device batch -> the graph's static inputs (d2d) -> replay
-            loss = e2e_state["graphed"](*batch, log=False)
+        g = e2e_state.get("graphed")
+        if g is not None:
+            # double-buffered graph replay: this step's batch was staged (pinned host -> the graph's idle input set, on a
+            # copy stream) during the previous step; stage the next one now, then replay
+            if i == 0:
+                g.stage((image_p, *gts_p))
+            loss = g.run(log=False)
+            g.stage((image_p, *gts_p))                          # H2D of step i+1 overlaps the compute of step i
         else:
+            for p in net.parameters():
+                p.grad = None
+            batch = next(loader)                                # this step's inputs, copied from pinned host memory
             loss = train_step(net, crit, *batch)
         loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)
         loss_evt[i & 1].record()
@@ -560,8 +566,8 @@ def run_ours(args):
         try:
             from real_time_helmet_detection_b200.train import GraphedTrainStep
             l0 = _lib.lib().hd_launch_count()
-            graphed = GraphedTrainStep(net, crit, image_d, *gts_d, warmup=0)
-            graph_launches = _lib.lib().hd_launch_count() - l0          # kernels recorded into the graph = per replay
+            graphed = GraphedTrainStep(net, crit, image_d, *gts_d, warmup=0, buffers=2)
+            graph_launches = (_lib.lib().hd_launch_count() - l0) // 2   # kernels recorded per graph = per replay (2 graphs)
         except Exception as exc:                                        # capture not possible: stay eager, say so
             graphed, eager = None, {"graph_error": f"{type(exc).__name__}: {str(exc)[:160]}"}
     if graphed is not None:
@@ -675,9 +681,11 @@ def run_ours(args):
                            "l2": "no explicit flush: ~10 GB of activations per step >> 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
-                        "how": ("train.GraphedTrainStep" if graphed is not None else "train.train_step") +
-                               " on pinned host batches via train.DevicePrefetcher (H2D of step i+1 "
-                               "overlaps step i); every step's loss is copied D2H and read on the host one step later"},
+                        "how": ("train.GraphedTrainStep.stage / run: pinned host batch -> H2D into the idle one of two static "
+                                "input sets on a copy stream (overlapping the previous step) -> CUDA-graph replay of the "
+                                "iteration" if graphed is not None else
+                                "train.train_step on pinned host batches via train.DevicePrefetcher (H2D of step i+1 "
+                                "overlaps step i)") + "; every step's loss is copied D2H and read on the host one step later"},
                 "e2e_device_collate": {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": "img/s",
                                        "h2d_bytes_per_step": collate.h2d_bytes * world, "ms_per_step": ms_u8 / args.steps,
                                        "how": "uint8 HWC images + padded box lists staged in pinned memory -> data.DeviceCollate "

@@ -83,16 +83,23 @@ def train_step(network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, 
 class GraphedTrainStep:
     """One training iteration (forward + fused loss + backward, train.py:97-134) recorded ONCE into a CUDA graph and
     replayed: the ~260 kernel launches, ~100 cross-stream event edges and the autograd bookkeeping of a step become
-    one `cudaGraphLaunch`. Shapes are fixed by the example batch; every call copies the new batch into the graph's static
-    input tensors (host or device sources) and replays. Parameter gradients land in `p.grad` (static views of the flat
-    gradient buffer, rewritten by each replay), so an optimizer step between calls works as usual; BatchNorm running
+    one `cudaGraphLaunch`. Shapes are fixed by the example batch. Parameter gradients land in `p.grad` (static views of
+    the flat gradient buffer of the replayed graph), so an optimizer step between calls works as usual; BatchNorm running
     statistics are updated by the replayed kernels exactly as in the eager step.
+
+    Two ways to feed it:
+      * `step(image, ghm, goff, gsize, gmask)`  - copies the batch (host or device tensors) into the static inputs on the
+        compute stream, replays, returns the loss;
+      * `stage(batch)` / `run()`                 - double-buffered: `buffers=2` input sets with one graph each; `stage`
+        copies the NEXT batch (e.g. pinned host tensors) into the idle set on a copy stream while `run()` replays the
+        graph of the set staged before, so the H2D copy of step i+1 overlaps the compute of step i with no extra
+        device-to-device copy.
 
     Single-GPU only (a NCCL exchange inside the backward node is not captured); the network must be in train() mode.
     """
 
     def __init__(self, network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, gt_mask, num_cls=2,
-                 normalized_coord=False, warmup=3):
+                 normalized_coord=False, warmup=3, buffers=1):
         if getattr(network, "grad_sync", None) is not None:
             raise RuntimeError("GraphedTrainStep: a gradient exchange hook is attached; graphs are single-GPU only")
         if not network.training:
@@ -100,47 +107,99 @@ class GraphedTrainStep:
         self.network, self.loss_calculator = network, loss_calculator
         self.num_cls, self.normalized_coord = num_cls, normalized_coord
         device = next(network.parameters()).device
-        self.static_in = [t.to(device, copy=True) for t in (image, gt_heatmap, gt_offset, gt_size, gt_mask)]
+        self.device = device
+        example = (image, gt_heatmap, gt_offset, gt_size, gt_mask)
+        self.sets = [[t.to(device, copy=True) for t in example] for _ in range(max(1, int(buffers)))]
+        self.static_in = self.sets[0]
         cur = torch.cuda.current_stream(device)
         side = torch.cuda.Stream(device=device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):                  # eager warm-up: arena, streams, events, kernel attributes
             for _ in range(warmup):
-                self._eager()
+                self._eager(self.sets[0])
         cur.wait_stream(side)
         torch.cuda.synchronize(device)
         pending = list(loss_calculator._pending)       # the capture must not leave graph-pool tensors in the log queue
-        for p in network.parameters():
-            p.grad = None
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager()
-            self.static_values = [v for v in loss_calculator._pending[len(pending):]]
-        loss_calculator._pending = pending
+        self.graphs, self.losses, self.values, self.grads = [], [], [], []
+        params = list(network.parameters())
+        for inputs in self.sets:
+            for p in params:
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._eager(inputs)
+            self.graphs.append(g)
+            self.losses.append(loss)
+            self.values.append(list(loss_calculator._pending[len(pending):]))
+            self.grads.append([p.grad for p in params])
+            loss_calculator._pending = list(pending)
+        self._params = params
+        self._cur = 0                                   # set whose graph `run()` replays next
+        self._staged = [None] * len(self.sets)          # copy-complete events
+        self._used = [None] * len(self.sets)            # replay-complete events
+        self._copy_stream = torch.cuda.Stream(device=device)
+        self.static_loss, self.static_values = self.losses[0], self.values[0]
 
-    def _eager(self):
+    def _eager(self, inputs):
         for p in self.network.parameters():
             p.grad = None
-        outputs = self.network(self.static_in[0])
+        outputs = self.network(inputs[0])
         S = outputs.shape[1]
         total = None
         for s in range(S):
             logits_s = outputs.squeeze(1) if S == 1 else outputs[:, s]
-            loss_s = self.loss_calculator.forward_logits(logits_s, *self.static_in[1:], num_cls=self.num_cls,
+            loss_s = self.loss_calculator.forward_logits(logits_s, *inputs[1:], num_cls=self.num_cls,
                                                          normalized_coord=self.normalized_coord)
             total = loss_s if total is None else total + loss_s
         total.backward()
         return total.detach()
 
+    def _replay(self, k, log):
+        self.graphs[k].replay()
+        if len(self.graphs) > 1:                        # p.grad must name the buffer THIS graph wrote
+            for p, g in zip(self._params, self.grads[k]):
+                p.grad = g
+        if log:                                         # LossCalculator.log keeps working: one small copy per stack
+            for v in self.values[k]:
+                self.loss_calculator._record(v.clone())
+        return self.losses[k]
+
     def __call__(self, image, gt_heatmap, gt_offset, gt_size, gt_mask, log=True):
-        for dst, src in zip(self.static_in, (image, gt_heatmap, gt_offset, gt_size, gt_mask)):
+        for dst, src in zip(self.sets[0], (image, gt_heatmap, gt_offset, gt_size, gt_mask)):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
-        if log:                                        # LossCalculator.log keeps working: one small copy per stack
-            for v in self.static_values:
-                self.loss_calculator._record(v.clone())
-        return self.static_loss.clone()
+        return self._replay(0, log).clone()
+
+    step = __call__
+
+    def stage(self, batch):
+        """Copy `batch` (5 tensors, e.g. pinned host memory) into the next idle input set on the copy stream."""
+        k = (self._cur + sum(e is not None for e in self._staged)) % len(self.sets)
+        if self._staged[k] is not None:
+            raise RuntimeError("GraphedTrainStep.stage: every input set already holds a staged batch; call run() first")
+        if self._used[k] is not None:
+            self._copy_stream.wait_event(self._used[k])          # the replay that last read this set has finished
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self.sets[k], batch):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._staged[k] = ev
+
+    def run(self, log=True):
+        """Replay the graph of the oldest staged input set; returns its loss tensor (static: clone to keep it)."""
+        k = self._cur
+        if self._staged[k] is None:
+            raise RuntimeError("GraphedTrainStep.run: no staged batch")
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged[k])
+        self._staged[k] = None
+        loss = self._replay(k, log)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._used[k] = ev
+        self._cur = (k + 1) % len(self.sets)
+        return loss
 
 
 class DevicePrefetcher:

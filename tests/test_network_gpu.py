@@ -293,3 +293,20 @@ def test_graphed_train_step_matches_eager(cuda_device):
         if "num_batches_tracked" in k:
             assert int(a) == int(b) == 3, k
     assert len(crits[2].log["total"]) == 3 and abs(crits[2].log["total"][-1] - lg) < 1e-4
+    # double-buffered feeding: stage() copies the next (pinned host) batch into the idle input set on a copy stream,
+    # run() replays the graph of the set staged before; p.grad follows the graph that ran
+    g2 = GraphedTrainStep(nets[2], crits[2], x0, *gts, buffers=2)
+    xs = [torch.randn(4, 3, 192, 192, generator=torch.Generator().manual_seed(50 + i)).pin_memory() for i in range(3)]
+    gts_h = [g.cpu().pin_memory() for g in gts]
+    g2.stage((xs[0], *gts_h))
+    for i in range(3):
+        loss = g2.run()
+        if i + 1 < 3:
+            g2.stage((xs[i + 1], *gts_h))
+        for p in nets[0].parameters():
+            p.grad = None
+        le = float(train_step(nets[0], crits[0], xs[i].to(cuda_device), *gts))
+        assert abs(float(loss) - le) <= 5e-3 * abs(le), (i, float(loss), le)
+        assert rel(flat(nets[2]), flat(nets[0])) <= 3.0 * noise + 2e-2, i
+    with pytest.raises(RuntimeError, match="no staged batch"):
+        g2.run()

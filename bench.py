@@ -439,19 +439,31 @@ def config3_line(torch, dev, peaks, steps=10, warmup=4):
                 p.grad = None
             train_step(net, crit, x, *gts)
 
-        for _ in range(warmup):
-            step()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        def time_it(fn):
+            for _ in range(warmup):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        ms_eager = time_it(step)
+        ms, launch = ms_eager, "eager (kernel by kernel)"
+        try:                                              # the same iteration replayed from a CUDA graph, as for config 2
+            from real_time_helmet_detection_b200.train import GraphedTrainStep
+            graphed = GraphedTrainStep(net, crit, x, *gts, warmup=0)
+            ms = time_it(lambda: graphed(*graphed.static_in, log=False))
+            launch = "CUDA graph replay (train.GraphedTrainStep)"
+        except Exception as exc:
+            launch += f" (graph capture failed: {type(exc).__name__})"
         ips = B / ms * 1e3
         return {"workload": "2-stack hourglass, 2 classes, 512x512, batch 16, bf16, train fwd + loss + bwd",
-                "value": ips, "unit": "img/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "value": ips, "unit": "img/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "launch": launch,
+                "eager_img_s": B / ms_eager * 1e3,
                 "step_frac_of_conv_roofline": ips * FLOPS_PER_IMG_TRAIN[2] / (peaks["bf16_tflops_sustained"] * 1e12)}
     except Exception as exc:
         return {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
@@ -558,11 +570,11 @@ def run_ours(args):
     warmup = max(3, args.warmup)
     for _ in range(warmup):
         step_device()
-    # Single GPU: the measured step is the same iteration replayed from a CUDA graph (train.GraphedTrainStep: one
-    # cudaGraphLaunch instead of ~260 kernel launches + ~100 cross-stream event edges; identical kernels and work). The
-    # eager step is timed as well and reported beside it. N > 1 stays eager (the NCCL exchange lives in the backward node).
+    # The measured step is the same iteration replayed from a CUDA graph (train.GraphedTrainStep: one cudaGraphLaunch
+    # instead of ~260 kernel launches + ~100 cross-stream event edges; identical kernels and work; for N > 1 the NCCL
+    # exchange inside the backward node is part of the recording). The eager step is timed as well and reported beside it.
     graphed, graph_launches, eager = None, 0, None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             from real_time_helmet_detection_b200.train import GraphedTrainStep
             l0 = _lib.lib().hd_launch_count()
@@ -570,6 +582,11 @@ def run_ours(args):
             graph_launches = (_lib.lib().hd_launch_count() - l0) // 2   # kernels recorded per graph = per replay (2 graphs)
         except Exception as exc:                                        # capture not possible: stay eager, say so
             graphed, eager = None, {"graph_error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    if world > 1:                                # every rank must take the same path
+        ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            graphed = None
     if graphed is not None:
         ms_eager, launches_eager, _, _ = timed(step_device, args.steps)
         eager = {"value": world * B * args.steps / (ms_eager * 1e-3), "unit": "img/s", "ms_per_step": ms_eager / args.steps,

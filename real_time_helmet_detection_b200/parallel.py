@@ -41,6 +41,9 @@ class FlatAllReduce:
         self.events = []                # timing: (bucket name, start event, end event)
         backend = dist.get_backend(process_group) if self.active() else None
         self._avg_op = self.active() and average and backend == "nccl"
+        # the collectives can be recorded into a CUDA graph (train.GraphedTrainStep) when they run on NCCL and no timing
+        # events are requested
+        self.capturable = (not self.active()) or (backend == "nccl" and not timing)
 
     def active(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1

@@ -95,13 +95,17 @@ class GraphedTrainStep:
         graph of the set staged before, so the H2D copy of step i+1 overlaps the compute of step i with no extra
         device-to-device copy.
 
-    Single-GPU only (a NCCL exchange inside the backward node is not captured); the network must be in train() mode.
+    Data parallel: the NCCL exchange of `parallel.FlatAllReduce` inside the backward node is recorded with the rest (NCCL
+    collectives are graph-capturable); every rank must build and replay its graph in lockstep. The network must be in
+    train() mode.
     """
 
     def __init__(self, network, loss_calculator, image, gt_heatmap, gt_offset, gt_size, gt_mask, num_cls=2,
                  normalized_coord=False, warmup=3, buffers=1):
-        if getattr(network, "grad_sync", None) is not None:
-            raise RuntimeError("GraphedTrainStep: a gradient exchange hook is attached; graphs are single-GPU only")
+        sync = getattr(network, "grad_sync", None)
+        if sync is not None and not getattr(sync, "capturable", False):
+            raise RuntimeError("GraphedTrainStep: the attached gradient exchange hook cannot be recorded into a CUDA graph "
+                               "(parallel.FlatAllReduce over NCCL can)")
         if not network.training:
             raise RuntimeError("GraphedTrainStep records the training-mode step: call network.train() first")
         self.network, self.loss_calculator = network, loss_calculator

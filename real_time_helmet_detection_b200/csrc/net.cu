@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <map>
 #include <vector>
 
 #include "hd_b200.h"
@@ -131,6 +132,9 @@ struct hd_net {
     // pinned staging slots for the job tables of forwards recorded into a CUDA graph (see upload_table)
     uint8_t* pinned = nullptr;
     int pinned_next = 0;
+    std::map<const void*, std::vector<uint8_t>> uploaded;   // device table -> host copy of what was last uploaded there
+    const void* last_ws = nullptr;
+    size_t last_ws_bytes = 0;
     ~hd_net() {
         if (pinned) cudaFreeHost(pinned);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
@@ -313,6 +317,13 @@ static void upload_table(hd_net* n, void* dst, const void* src, size_t bytes) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(n->stream, &st) != cudaSuccess) { n->rc = fail(HD_ERR_CUDA, "net: cudaStreamIsCapturing failed"); return; }
     if (st == cudaStreamCaptureStatusActive) {
+        // A table identical to the one already uploaded to this slot (the eager warm-up pass that precedes every capture
+        // uses the same parameters and arena) needs no copy node at all. That matters beyond the saved node: a host-to-
+        // device copy node shares the copy engine with the application's own H2D traffic - the next batch being staged
+        // while this graph replays - and queued behind a 115 MB batch copy it stalled the first kernels of the step by
+        // ~1.4 ms (measured: 13.7 vs 12.3 ms per step with pinned-host staging).
+        auto it = n->uploaded.find(dst);
+        if (it != n->uploaded.end() && it->second.size() == bytes && memcmp(it->second.data(), src, bytes) == 0) return;
         if (!n->pinned || n->pinned_next >= kPinnedSlots || bytes > kPinnedSlotBytes) {
             n->rc = fail(HD_ERR_UNSUPPORTED, "net: cannot record this forward into a CUDA graph (%s)",
                          !n->pinned ? "run one eager forward first" : "more than 16 graphs captured on one network");
@@ -324,6 +335,8 @@ static void upload_table(hd_net* n, void* dst, const void* src, size_t bytes) {
     }
     if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, n->stream) != cudaSuccess)
         n->rc = fail(HD_ERR_CUDA, "net_forward: upload of a job table failed");
+    else
+        n->uploaded[dst].assign(static_cast<const uint8_t*>(src), static_cast<const uint8_t*>(src) + bytes);
 }
 
 static void pack_weights(hd_net* n, bool need_dgrad) {
@@ -943,6 +956,10 @@ extern "C" int hd_net_forward(hd_net* n, const hd_unit_ptrs* units, int n_units,
         return fail(HD_ERR_CUDA, "net_forward: cannot create the second lane's stream");
     static const bool single_lane = getenv("HD_SINGLE_LANE") != nullptr;   // debug knob: everything on one stream
     n->alt.stream = single_lane ? stream : n->alt_stream;
+    if (workspace != n->last_ws || workspace_bytes != n->last_ws_bytes) {     // another arena: nothing is known about its contents
+        n->uploaded.clear();
+        n->last_ws = workspace; n->last_ws_bytes = workspace_bytes;
+    }
     plan(n, reinterpret_cast<uint8_t*>(workspace), workspace_bytes, B, H, W, training != 0, &head);
     n->B = B; n->H = H; n->W = W;
     // capacity check with a dry pass first (cheap: pointer arithmetic only)

@@ -119,7 +119,7 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):                  # eager warm-up: arena, streams, events, kernel attributes
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):        # at least one: the capture relies on what an eager pass set up
                 self._eager(self.sets[0])
         cur.wait_stream(side)
         torch.cuda.synchronize(device)

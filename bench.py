@@ -729,8 +729,22 @@ def run_ours(args):
                                          if hook.overlap else "one flat all-reduce after the backward pass")}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Teardown. CUDA graphs that recorded NCCL collectives keep communicator resources alive, and destroying the
+        # process group under them was seen to hang (round 2: the JSON line was out, then the run sat until its timeout).
+        # So: drop the graphs first, and bound the whole teardown - the measurement is complete at this point.
+        import gc
+        sys.stdout.flush()
+        graphed = None
+        e2e_state.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            sys.stdout.flush()
+            os._exit(0)
 
 
 def main():

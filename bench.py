@@ -577,9 +577,8 @@ def run_ours(args):
     if not args.no_graph:
         try:
             from real_time_helmet_detection_b200.train import GraphedTrainStep
-            l0 = _lib.lib().hd_launch_count()
             graphed = GraphedTrainStep(net, crit, image_d, *gts_d, warmup=0, buffers=2)
-            graph_launches = (_lib.lib().hd_launch_count() - l0) // 2   # kernels recorded per graph = per replay (2 graphs)
+            graph_launches = graphed.kernels_per_replay                 # library kernels recorded into one graph = per replay
         except Exception as exc:                                        # capture not possible: stay eager, say so
             graphed, eager = None, {"graph_error": f"{type(exc).__name__}: {str(exc)[:160]}"}
     if world > 1:                                # every rank must take the same path

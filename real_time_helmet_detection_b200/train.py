@@ -126,12 +126,15 @@ class GraphedTrainStep:
         pending = list(loss_calculator._pending)       # the capture must not leave graph-pool tensors in the log queue
         self.graphs, self.losses, self.values, self.grads = [], [], [], []
         params = list(network.parameters())
+        from . import _lib
         for inputs in self.sets:
             for p in params:
                 p.grad = None
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.lib().hd_launch_count()
             with torch.cuda.graph(g):
                 loss = self._eager(inputs)
+            self.kernels_per_replay = int(_lib.lib().hd_launch_count() - l0)   # library kernels recorded into one graph
             self.graphs.append(g)
             self.losses.append(loss)
             self.values.append(list(loss_calculator._pending[len(pending):]))

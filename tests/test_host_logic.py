@@ -75,3 +75,44 @@ def test_loss_log_contract():
     assert crit.log == {"hm": [], "offset": [], "size": [], "total": []}
     crit.log = {k: [1.0, 3.0] for k in ("hm", "offset", "size", "total")}
     assert crit.get_log() == "hm:  2.00, offset:  2.00, size:  2.00, total:  2.00"
+
+
+def test_product_never_imports_oracle_or_baseline():
+    """The oracle (oracle/) and the staged reference / library-bar helpers (baseline/) are test and measurement
+    infrastructure: no module of the package, the runner or the C sources may import, include or execute them."""
+    pkg = os.path.join(ROOT, "real_time_helmet_detection_b200")
+    offenders = []
+    for base, _dirs, files in os.walk(pkg):
+        if os.path.basename(base) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                continue
+            text = open(os.path.join(base, f), errors="ignore").read()
+            if re.search(r"^\s*(from|import)\s+(oracle|baseline)\b", text, re.M) or "oracle/" in text and f.endswith((".cu", ".h", ".cpp")):
+                offenders.append(os.path.relpath(os.path.join(base, f), ROOT))
+    runner = open(os.path.join(ROOT, "runner", "hd_infer.cpp")).read()
+    assert "oracle" not in runner and "baseline" not in runner
+    assert not offenders, offenders
+
+
+def test_reference_staging_and_shims_layout():
+    """tools/stage_reference.py keeps the reference out of the history (baseline/_ref is git-ignored), and the three shim
+    modules of INTEGRATION.md exist with the reference's flat names."""
+    gi = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "baseline/_ref/" in gi
+    shims = os.path.join(ROOT, "real_time_helmet_detection_b200", "shims")
+    assert sorted(f for f in os.listdir(shims) if f.endswith(".py")) == ["hourglass.py", "loss.py", "transform.py"]
+    from baseline import refload
+    if refload.available():                      # build container: the staged copies are the unmodified files
+        import hashlib
+        import json
+        man = json.load(open(os.path.join(refload.REF, "MANIFEST.json")))
+        for name, digest in man["files"].items():
+            assert hashlib.sha256(open(os.path.join(refload.REF, name), "rb").read()).hexdigest() == digest, name
+            ref = os.path.join("/root/reference", name)
+            if os.path.exists(ref):
+                assert open(ref, "rb").read() == open(os.path.join(refload.REF, name), "rb").read(), name
+        diff = open(os.path.join(refload.REF, "patched", "squeeze_patch.diff")).read()
+        changed = [l for l in diff.splitlines() if l[:1] in "+-" and l[:3] not in ("+++", "---")]
+        assert len(changed) == 4 and all("squeeze" in l for l in changed)       # the one-token fix, twice

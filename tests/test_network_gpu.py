@@ -287,9 +287,12 @@ def test_graphed_train_step_matches_eager(cuda_device):
         assert torch.isfinite(gg).all()
         noise = rel(gb, ga)
         assert rel(gg, ga) <= 3.0 * noise + 1e-2, (i, rel(gg, ga), noise)
+    sd_b = nets[1].state_dict()
     for (k, a), (_, b) in zip(nets[0].state_dict().items(), nets[2].state_dict().items()):
         if "running" in k:
-            assert torch.allclose(a, b, rtol=5e-3, atol=2e-3), k     # deep levels: bf16 activations, few samples
+            # deep levels: bf16 activations, 36 samples per channel - the bar is again the eager-vs-eager distance
+            floor = 3.0 * float((a - sd_b[k]).abs().max())
+            assert float((a - b).abs().max()) <= floor + 2e-3 + 5e-3 * float(a.abs().max()), k
         if "num_batches_tracked" in k:
             assert int(a) == int(b) == 3, k
     assert len(crits[2].log["total"]) == 3 and abs(crits[2].log["total"][-1] - lg) < 1e-4

@@ -219,6 +219,16 @@ int hd_bn_add_relu_pool2(const void* y2, const float* s2, const float* b2, const
                          const float* bs, void* pooled, void* idx, int N, int H, int W, int C, hd_stream_t stream);
 int hd_maxpool2_bwd_idx(const void* idx, const void* dpool, const void* add1, const void* add2, void* dx, int N, int H,
                         int W, int C, hd_stream_t stream);
+/* Backward of that fused tail WITHOUT materialising the routed, masked gradient g = route(dpool, idx) * (pre > 0)
+ * at the un-pooled size (autograd of hourglass.py:125-127 + :166): both BatchNorms' reduction (+ fused finalize, as
+ * hd_bn_bwd_reduce_fin) and their apply (dy = a*g + b*y2 + c, dys = as*g + bs*ys + cs) read dpool [N][H/2][W/2][C] and
+ * idx directly. H, W are the UN-pooled sizes; sc/sh, sc_s/sh_s the two BN scale/shift vectors of the forward pass. */
+int hd_bn_bwd_reduce_pool_fin(const void* dpool, const void* idx, const float* sc, const float* sh, const float* sc_s,
+                              const float* sh_s, const void* y2, const void* ys, float* sums, int N, int H, int W, int C,
+                              const hd_bn_bwd_fuse* fin, hd_stream_t stream);
+int hd_bn_bwd_apply_pool(const void* dpool, const void* idx, const float* sc, const float* sh, const float* sc_s,
+                         const float* sh_s, const void* y2, const void* ys, const float* coef, const float* coef_s,
+                         void* dy, void* dys, int N, int H, int W, int C, hd_stream_t stream);
 int hd_sum2x2(const void* dout, void* dlow, int N, int H, int W, int C, hd_stream_t stream);
 int hd_add(const void* a, const void* b, const void* c, void* out, long long nelem, hd_stream_t stream);
 int hd_colsum(const void* x, float* out, long long npix, int C, int cs, hd_stream_t stream);

@@ -751,6 +751,192 @@ __global__ void __launch_bounds__(256, SECOND ? 2 : (U >= 4 ? 2 : (U == 2 ? 3 : 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-branch BN backward BEHIND the fused relu + 2x2 max pool of PreLayer's Residual(64,128) (bn_add_relu_pool_kernel):
+//   g[window k] = (k == idx ? dpool : 0) * (bn(y) + bn_s(ys) > 0)
+// is never materialised. Both kernels walk the POOLED tensor - one thread = 8 channels of one 2x2 window, all eight
+// 16-byte loads of y / ys in flight before the first use - and read dpool (134 MB at 256x256, B = 32) + idx (67 MB)
+// where the unfused sequence wrote the routed gradient (537 MB, hd_maxpool2_bwd_idx) and read it back twice.
+// Same arithmetic, per element, as bn_bwd_reduce_kernel<true,true> / bn_bwd_apply_kernel<true,false> on that tensor.
+__device__ __forceinline__ void pool_window(uint32_t i, int cvec_log2, int Ho, int Wo, int W, int C, int c0, size_t offs[4]) {
+    const uint32_t pix = i >> cvec_log2;
+    const uint32_t ox = pix % Wo, t = pix / Wo;
+    const uint32_t oy = t % Ho, n = t / Ho;
+    const size_t o00 = ((static_cast<size_t>(n) * (2 * Ho) + 2 * oy) * W + 2 * ox) * C + c0;
+    offs[0] = o00; offs[1] = o00 + C; offs[2] = o00 + static_cast<size_t>(W) * C; offs[3] = offs[2] + C;
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_pool_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
+                          const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ sc_s,
+                          const float* __restrict__ sh_s, const __nv_bfloat16* __restrict__ y,
+                          const __nv_bfloat16* __restrict__ ys, float* __restrict__ sums, uint32_t nvec, int Ho, int Wo,
+                          int C, int cvec_log2, const hd_bn_bwd_fuse fin) {
+    pdl_prologue();
+    __shared__ __align__(16) float red[3 * 256];
+    const int cvec = 1 << cvec_log2, W = 2 * Wo;
+    const int c0 = static_cast<int>(threadIdx.x & (cvec - 1)) << 3;
+    float k0[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { k0[j] = sc[c0 + j]; k1[j] = sh[c0 + j]; k2[j] = sc_s[c0 + j]; k3[j] = sh_s[c0 + j]; }
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+    float a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = a2[j] = 0.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        size_t offs[4];
+        pool_window(i, cvec_log2, Ho, Wo, W, C, c0, offs);
+        uint4 ra[4], rb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ra[k] = ldg16(y + offs[k]); rb[k] = ldg16(ys + offs[k]); }
+        const F8 g = load8(dpool + static_cast<size_t>(i) * 8);
+        const uint2 w = *reinterpret_cast<const uint2*>(idx + static_cast<size_t>(i) * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const F8 a = cvt8(ra[k]), b = cvt8(rb[k]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t sel = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xffu;
+                const float pre = fmaf(a.v[j], k0[j], k1[j]) + fmaf(b.v[j], k2[j], k3[j]);
+                const float gj = (sel == static_cast<uint32_t>(k) && pre > 0.f) ? g.v[j] : 0.f;
+                a0[j] += gj;
+                a1[j] = fmaf(gj, a.v[j], a1[j]);
+                a2[j] = fmaf(gj, b.v[j], a2[j]);
+            }
+        }
+    }
+    __syncthreads();
+    // block reduction + "last CTA builds the coefficients", as in bn_bwd_reduce_kernel<true, .>
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (int o2 = cvec; o2 < 32; o2 <<= 1) {
+            a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o2);
+            a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o2);
+            a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o2);
+        }
+    }
+    if (static_cast<int>(threadIdx.x & 31) < cvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&red[c0 + j], a0[j]);
+            atomicAdd(&red[C + c0 + j], a1[j]);
+            atomicAdd(&red[2 * C + c0 + j], a2[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) atomicAdd(sums + c, red[c]);
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float S0 = __ldcg(sums + c);
+        {
+            const float g = fin.gamma[c], r = fin.rstd[c], m = fin.mean[c];
+            const float S1 = r * (__ldcg(sums + C + c) - m * S0);
+            fin.coef[c] = g * r;
+            fin.coef[C + c] = -g * r * r * S1 / fin.count;
+            fin.coef[2 * C + c] = g * r * (m * r * S1 - S0) / fin.count;
+            if (fin.dgamma) fin.dgamma[c] = S1;
+            if (fin.dbeta) fin.dbeta[c] = S0;
+        }
+        {
+            const float g = fin.gamma_s[c], r = fin.rstd_s[c], m = fin.mean_s[c];
+            const float S1 = r * (__ldcg(sums + 2 * C + c) - m * S0);
+            fin.coef_s[c] = g * r;
+            fin.coef_s[C + c] = -g * r * r * S1 / fin.count;
+            fin.coef_s[2 * C + c] = g * r * (m * r * S1 - S0) / fin.count;
+            if (fin.dgamma_s) fin.dgamma_s[c] = S1;
+            if (fin.dbeta_s) fin.dbeta_s[c] = S0;
+        }
+        sums[c] = 0.f;
+        sums[C + c] = 0.f;
+        sums[2 * C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *fin.counter = 0u;
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_pool_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
+                         const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ sc_s,
+                         const float* __restrict__ sh_s, const __nv_bfloat16* __restrict__ y,
+                         const __nv_bfloat16* __restrict__ ys, const float* __restrict__ coef,
+                         const float* __restrict__ coef_s, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
+                         uint32_t nvec, int Ho, int Wo, int C, int cvec_log2) {
+    pdl_prologue();
+    __shared__ __align__(16) float p[10][256];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        p[0][i] = coef[i]; p[1][i] = coef[C + i]; p[2][i] = coef[2 * C + i];
+        p[3][i] = coef_s[i]; p[4][i] = coef_s[C + i]; p[5][i] = coef_s[2 * C + i];
+        p[6][i] = sc[i]; p[7][i] = sh[i]; p[8][i] = sc_s[i]; p[9][i] = sh_s[i];
+    }
+    __syncthreads();
+    const int cvec = 1 << cvec_log2, W = 2 * Wo;
+    const int c0 = static_cast<int>(threadIdx.x & (cvec - 1)) << 3;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        size_t offs[4];
+        pool_window(i, cvec_log2, Ho, Wo, W, C, c0, offs);
+        uint4 ra[4], rb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ra[k] = ldg16(y + offs[k]); rb[k] = ldg16(ys + offs[k]); }
+        const F8 g = load8(dpool + static_cast<size_t>(i) * 8);
+        const uint2 w = *reinterpret_cast<const uint2*>(idx + static_cast<size_t>(i) * 8);
+        // pass 1: which of the 4 x 8 window elements carry the pooled gradient (bit k*8+j)
+        uint32_t on = 0;
+        {
+            float k0[8], k1[8], k2[8], k3[8];
+            lds8(p[6], c0, k0); lds8(p[7], c0, k1); lds8(p[8], c0, k2); lds8(p[9], c0, k3);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const F8 a = cvt8(ra[k]), b = cvt8(rb[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t sel = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xffu;
+                    const float pre = fmaf(a.v[j], k0[j], k1[j]) + fmaf(b.v[j], k2[j], k3[j]);
+                    on |= (sel == static_cast<uint32_t>(k) && pre > 0.f ? 1u : 0u) << (k * 8 + j);
+                }
+            }
+        }
+        // pass 2: dy = a*g + b*y + c per branch. (The compiler barriers keep the three constant sets from being live at the
+        // same time: 80 floats of per-channel constants + eight 16-byte loads do not fit 128 registers.)
+        asm volatile("" ::: "memory");
+        {
+            float ka[8], kb[8], kc[8];
+            lds8(p[0], c0, ka); lds8(p[1], c0, kb); lds8(p[2], c0, kc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const F8 a = cvt8(ra[k]);
+                F8 r;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gj = ((on >> (k * 8 + j)) & 1u) ? g.v[j] : 0.f;
+                    r.v[j] = fmaf(ka[j], gj, fmaf(kb[j], a.v[j], kc[j]));
+                }
+                store8(dy + offs[k], r);
+            }
+        }
+        asm volatile("" ::: "memory");
+        {
+            float ka[8], kb[8], kc[8];
+            lds8(p[3], c0, ka); lds8(p[4], c0, kb); lds8(p[5], c0, kc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const F8 b = cvt8(rb[k]);
+                F8 r;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gj = ((on >> (k * 8 + j)) & 1u) ? g.v[j] : 0.f;
+                    r.v[j] = fmaf(ka[j], gj, fmaf(kb[j], b.v[j], kc[j]));
+                }
+                store8(dys + offs[k], r);
+            }
+        }
+    }
+}
+
 // dx = route(dpool) [+ add1] [+ add2]; the pooled gradient goes to the first maximum of each 2x2 window in
 // row-major scan order (PyTorch max_pool2d backward semantics).
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dpool,
@@ -1153,6 +1339,51 @@ extern "C" int hd_bn_add_relu_pool2(cvp y2, const float* s2, const float* b2, cv
     HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_pool_kernel, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2, BF(ys), ss,
                                  bs,
                                  BFW(pooled), reinterpret_cast<uint8_t*>(idx), N, H, W, C));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+static int pool_dual_shape(const char* who, int N, int H, int W, int C, uint32_t* nvec, int* cvec_log2) {
+    HD_REQUIRE((C == 64 || C == 128 || C == 256) && H % 2 == 0 && W % 2 == 0 && N >= 0, "%s: shape (%d,%d,%d,%d)", who, N, H, W, C);
+    const size_t nv = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    HD_REQUIRE(nv < (1ull << 31), "%s: %zu pooled vectors exceed the 32-bit index of this kernel", who, nv);
+    *nvec = static_cast<uint32_t>(nv);
+    *cvec_log2 = C == 64 ? 3 : (C == 128 ? 4 : 5);
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_reduce_pool_fin(cvp dpool, cvp idx, const float* sc, const float* sh, const float* sc_s,
+                                         const float* sh_s, cvp y, cvp ys, float* sums, int N, int H, int W, int C,
+                                         const hd_bn_bwd_fuse* fin, cudaStream_t stream) {
+    HD_REQUIRE(dpool && idx && sc && sh && sc_s && sh_s && y && ys && sums, "bn_bwd_reduce_pool: null argument");
+    HD_REQUIRE(fin && fin->coef && fin->coef_s && fin->counter && fin->gamma && fin->mean && fin->rstd && fin->gamma_s &&
+                   fin->mean_s && fin->rstd_s && fin->count > 0.f,
+               "bn_bwd_reduce_pool: incomplete finalize block");
+    uint32_t nvec = 0;
+    int lg = 0;
+    if (int rc = pool_dual_shape("bn_bwd_reduce_pool", N, H, W, C, &nvec, &lg)) return rc;
+    if (nvec == 0) return HD_OK;
+    const int blocks = grid_for(nvec, 256 * 2, sm_count() * 2);
+    HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_pool_kernel, blocks, 256, 0, stream, BF(dpool),
+                                 reinterpret_cast<const uint8_t*>(idx), sc, sh, sc_s, sh_s, BF(y), BF(ys), sums, nvec, H / 2,
+                                 W / 2, C, lg, *fin));
+    HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_apply_pool(cvp dpool, cvp idx, const float* sc, const float* sh, const float* sc_s,
+                                    const float* sh_s, cvp y, cvp ys, const float* coef, const float* coef_s, void* dy,
+                                    void* dys, int N, int H, int W, int C, cudaStream_t stream) {
+    HD_REQUIRE(dpool && idx && sc && sh && sc_s && sh_s && y && ys && coef && coef_s && dy && dys,
+               "bn_bwd_apply_pool: null argument");
+    uint32_t nvec = 0;
+    int lg = 0;
+    if (int rc = pool_dual_shape("bn_bwd_apply_pool", N, H, W, C, &nvec, &lg)) return rc;
+    if (nvec == 0) return HD_OK;
+    const int blocks = grid_for(nvec, 256 * 2, sm_count() * 2);
+    HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_pool_kernel, blocks, 256, 0, stream, BF(dpool),
+                                 reinterpret_cast<const uint8_t*>(idx), sc, sh, sc_s, sh_s, BF(y), BF(ys), coef, coef_s,
+                                 BFW(dy), BFW(dys), nvec, H / 2, W / 2, C, lg));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }

@@ -657,8 +657,11 @@ static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H
 }
 
 // BN (+ReLU) backward of one unit: g = dout * (out > 0) -> dy (and the skip branch / g when requested)
+// pool_idx != nullptr: `dout` is the gradient of the 2x2-POOLED block output and pool_idx the argmax the fused forward
+// tail stored (two-branch tails only): the BN-backward kernels route it themselves (hd_bn_bwd_*_pool)
 static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, const bf16* y, bf16* dy, int us,
-                        const bf16* ys, bf16* dys, bf16* gout, const uint8_t* mask = nullptr) {
+                        const bf16* ys, bf16* dys, bf16* gout, const uint8_t* mask = nullptr,
+                        const uint8_t* pool_idx = nullptr, int pB = 0, int pH = 0, int pW = 0) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
     const int C = u.cout;
@@ -684,6 +687,13 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
     // instead of reading the stored block output (saves a 537 MB read per kernel at 256x256)
     const float* sc_s = s ? s->bnp : nullptr;
     const float* sh_s = s ? s->bnp + C : nullptr;
+    if (pool_idx) {
+        if (!s) { if (n->rc == 0) n->rc = fail(HD_ERR_INVALID, "net: pooled BN backward needs a two-branch tail"); return; }
+        RUN(hd_bn_bwd_reduce_pool_fin(dout, pool_idx, u.bnp, u.bnp + C, sc_s, sh_s, y, ys, sums, pB, pH, pW, C, &fin, n->stream));
+        RUN(hd_bn_bwd_apply_pool(dout, pool_idx, u.bnp, u.bnp + C, sc_s, sh_s, y, ys, coef, coef_s, dy, dys, pB, pH, pW, C,
+                                 n->stream));
+        return;
+    }
     // small maps (the deep hourglass levels): one launch instead of two, see bn_bwd_fused_small_kernel
     static const long long fused_max = getenv("HD_BN_FUSED_SMALL_MAX") ? atoll(getenv("HD_BN_FUSED_SMALL_MAX")) : 32768;
     unsigned int* epoch = reinterpret_cast<unsigned int*>(n->small + 9 * 256) + 1;
@@ -703,7 +713,7 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
                         u.npix, C, n->stream));
 }
 
-static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
+static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B, const uint8_t* pool_idx = nullptr) {
     ResSaved& r = n->res[ri];
     const int H = r.H, W = r.W;
     const size_t mark = n->bw.off;
@@ -713,7 +723,7 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B) {
     bf16* dYs = r.us >= 0 ? reinterpret_cast<bf16*>(n->wg.alloc(bytes_o)) : nullptr;
     bf16* dY1 = reinterpret_cast<bf16*>(n->wg.alloc(bytes_o));
     bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
-    bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G, r.Mask);
+    bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G, r.Mask, pool_idx, B, H, W);
     bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
     // The readiness event is recorded AFTER the dgrad launch on purpose: dgrad and wgrad are both persistent
@@ -855,12 +865,18 @@ static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
     if (!(stages & 2)) return;
     bf16* dP = n->dX_pre;
     // PreLayer, 256x256 part
-    bf16* dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
-    if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    // The pool's backward is folded into the BN backward of the block before it when that block's tail was fused with the
+    // pool in the forward pass: the routed gradient (537 MB at 256x256, B = 32) is then neither written nor read
+    // (HD_NO_POOL_BWD_FUSE=1: the separate hd_maxpool2_bwd_idx launch of the first version)
+    static const bool no_pool_bwd_fuse = getenv("HD_NO_POOL_BWD_FUSE") != nullptr;
+    const bool fold_pool = n->R1idx != nullptr && !no_pool_bwd_fuse;
+    bf16* dR1 = fold_pool ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
+    if (fold_pool) {}
+    else if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
     else RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
     phase_mark(n, "pool bwd");
     bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
-    residual_bwd(n, n->r_pre1, dR1, dZ0, B);
+    residual_bwd(n, n->r_pre1, fold_pool ? dP : dR1, dZ0, B, fold_pool ? n->R1idx : nullptr);
     phase_mark(n, "pre1@256 bwd");
     bf16* dY0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     bn_bwd_unit(n, 0, dZ0, nullptr, n->Y0, dY0, -1, nullptr, nullptr, nullptr);

@@ -363,3 +363,76 @@ def test_bn_backward_fused_small(cuda_device, N, H, W):
     torch.cuda.synchronize()
     assert int(words[0]) == 0 and int(words[1]) == 6             # ticket left at zero, six launches raised the epoch
     assert float(sums.abs().max()) == 0.0                        # accumulators left zeroed
+
+
+@pytest.mark.parametrize("C,N,H,W", [(128, 2, 16, 24), (128, 3, 64, 64), (64, 1, 8, 8), (128, 1, 2, 2)])
+def test_bn_backward_through_fused_pool(cuda_device, C, N, H, W):
+    """hd_bn_bwd_reduce_pool_fin / hd_bn_bwd_apply_pool (the pool's backward folded into the two-branch BN backward of
+    PreLayer's Residual(64,128)) == hd_maxpool2_bwd_idx -> hd_bn_bwd_reduce_fin -> hd_bn_bwd_apply on the routed gradient:
+    coefficients / dgamma / dbeta to fp32 summation-order noise, dy / dys BIT-exact when both applies get the same
+    coefficients; the scratch (sums, ticket) is left ready for the next launch."""
+    import ctypes
+    from real_time_helmet_detection_b200 import ops, _lib
+
+    class Fuse(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_void_p) for k in ("gamma", "mean", "rstd", "coef", "dgamma", "dbeta", "gamma_s", "mean_s",
+                                                   "rstd_s", "coef_s", "dgamma_s", "dbeta_s")] + \
+                   [("count", ctypes.c_float), ("counter", ctypes.c_void_p)]
+
+    g = torch.Generator().manual_seed(C + H + N)
+    d = cuda_device
+    L = _lib.lib()
+    npix = N * H * W
+    y2, ys = (nhwc(bf(torch.randn(N, C, H, W, generator=g)), d) for _ in range(2))
+
+    def bnp():      # scale | shift | mean | rstd
+        return torch.stack([torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5,
+                            torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5]).to(d)
+    b2, bs = bnp(), bnp()
+    gamma, gamma_s = ((torch.rand(C, generator=g) + 0.5).to(d) for _ in range(2))
+    pooled, idx = ops.bn_add_relu_pool2(y2, b2[:2].contiguous(), ys, bs[:2].contiguous())
+    dpool = nhwc(bf(torch.randn(N, C, H // 2, W // 2, generator=g)), d)
+
+    def scratch():
+        s = torch.zeros(16 * 256, device=d)
+        return s, s[:768], s[768:1536], s[1536:2304], s[9 * 256:].view(torch.int32)
+
+    def fuse(coef, coef_s, words, outs):
+        f = Fuse()
+        f.gamma, f.mean, f.rstd = gamma.data_ptr(), b2[2].data_ptr(), b2[3].data_ptr()
+        f.gamma_s, f.mean_s, f.rstd_s = gamma_s.data_ptr(), bs[2].data_ptr(), bs[3].data_ptr()
+        f.coef, f.coef_s = coef.data_ptr(), coef_s.data_ptr()
+        f.dgamma, f.dbeta, f.dgamma_s, f.dbeta_s = (o.data_ptr() for o in outs)
+        f.count, f.counter = float(npix), words.data_ptr()
+        return f
+
+    # unfused: route, then the two-branch reduce / apply with the mask rebuilt from y2 / ys
+    dout = ops.maxpool2_bwd_idx(idx, dpool)
+    sA, sumsA, coefA, coefsA, wordsA = scratch()
+    outsA = [torch.empty(C, device=d) for _ in range(4)]
+    fA = fuse(coefA, coefsA, wordsA, outsA)
+    _lib.check(L.hd_bn_bwd_reduce_fin(_lib.ptr(dout), None, _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(bs[0]), _lib.ptr(bs[1]),
+                                      _lib.ptr(y2), _lib.ptr(ys), _lib.ptr(sumsA), npix, C, ctypes.byref(fA), _lib.stream()))
+    dyA, dysA = torch.empty_like(y2), torch.empty_like(y2)
+    _lib.check(L.hd_bn_bwd_apply(_lib.ptr(dout), None, _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(bs[0]), _lib.ptr(bs[1]),
+                                 _lib.ptr(y2), _lib.ptr(coefA), _lib.ptr(dyA), _lib.ptr(ys), _lib.ptr(coefsA), _lib.ptr(dysA),
+                                 None, npix, C, _lib.stream()))
+    # folded
+    sB, sumsB, coefB, coefsB, wordsB = scratch()
+    outsB = [torch.empty(C, device=d) for _ in range(4)]
+    fB = fuse(coefB, coefsB, wordsB, outsB)
+    for rep in range(2):
+        _lib.check(L.hd_bn_bwd_reduce_pool_fin(_lib.ptr(dpool), _lib.ptr(idx), _lib.ptr(b2[0]), _lib.ptr(b2[1]),
+                                               _lib.ptr(bs[0]), _lib.ptr(bs[1]), _lib.ptr(y2), _lib.ptr(ys), _lib.ptr(sumsB),
+                                               N, H, W, C, ctypes.byref(fB), _lib.stream()))
+        for a, b in zip(outsA, outsB):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-3 * float(a.abs().max()) + 1e-6)
+        assert torch.allclose(coefA[:3 * C], coefB[:3 * C], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(coefsA[:3 * C], coefsB[:3 * C], rtol=1e-4, atol=1e-5)
+        torch.cuda.synchronize()
+        assert int(wordsB[0]) == 0 and float(sumsB.abs().max()) == 0.0
+    dyB, dysB = torch.empty_like(y2), torch.empty_like(y2)
+    _lib.check(L.hd_bn_bwd_apply_pool(_lib.ptr(dpool), _lib.ptr(idx), _lib.ptr(b2[0]), _lib.ptr(b2[1]), _lib.ptr(bs[0]),
+                                      _lib.ptr(bs[1]), _lib.ptr(y2), _lib.ptr(ys), _lib.ptr(coefA), _lib.ptr(coefsA),
+                                      _lib.ptr(dyB), _lib.ptr(dysB), N, H, W, C, _lib.stream()))
+    assert torch.equal(dyA, dyB) and torch.equal(dysA, dysB)

@@ -229,6 +229,17 @@ int hd_bn_bwd_reduce_pool_fin(const void* dpool, const void* idx, const float* s
 int hd_bn_bwd_apply_pool(const void* dpool, const void* idx, const float* sc, const float* sh, const float* sc_s,
                          const float* sh_s, const void* y2, const void* ys, const float* coef, const float* coef_s,
                          void* dy, void* dys, int N, int H, int W, int C, hd_stream_t stream);
+/* Data-gradient convolution that ALSO produces the BatchNorm-backward statistics of its consumer (autograd of
+ * hourglass.py:120-123: conv2's dgrad writes dZ1, the gradient behind conv1's BN + ReLU): out = conv(x) as
+ * hd_conv2d_igemm (NHWC bf16, cout == 128 dense), and with g = out * (y * act_scale + act_shift > 0) the epilogue
+ * accumulates sums[0][c] += sum g, sums[1][c] += sum g * y; the last CTA writes the coefficients / dgamma / dbeta of `fin`
+ * and re-zeroes `sums` - exactly what hd_bn_bwd_reduce_fin(out, NULL, act_scale, act_shift, ..., y, ...) would leave, so
+ * hd_bn_bwd_apply can follow directly and the reduction pass over out and y disappears. Only shapes that run on the
+ * transposed halo kernel (hd_conv2d_igemm_halo_eligible() == 1); y: NHWC bf16 of the output's shape. */
+int hd_conv2d_igemm_halo_eligible(int N, int H, int W, int cout, int ksize);
+int hd_conv2d_igemm_bwdstat(const void* x, const void* w_packed, void* out, int N, int H, int W, int cin, int cout,
+                            int ksize, const void* y, const float* act_scale, const float* act_shift, float* sums,
+                            const hd_bn_bwd_fuse* fin, hd_stream_t stream);
 int hd_sum2x2(const void* dout, void* dlow, int N, int H, int W, int C, hd_stream_t stream);
 int hd_add(const void* a, const void* b, const void* c, void* out, long long nelem, hd_stream_t stream);
 int hd_colsum(const void* x, float* out, long long npix, int C, int cs, hd_stream_t stream);

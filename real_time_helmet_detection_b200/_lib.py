@@ -64,6 +64,8 @@ _SIGNATURES = {
     "hd_maxpool2_bwd_idx": (I, [P, P, P, P, P, I, I, I, I, P]),
     "hd_bn_bwd_reduce_pool_fin": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, P, P]),
     "hd_bn_bwd_apply_pool": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
+    "hd_conv2d_igemm_halo_eligible": (I, [I, I, I, I, I]),
+    "hd_conv2d_igemm_bwdstat": (I, [P, P, P, I, I, I, I, I, I, P, P, P, P, P, P]),
     "hd_sum2x2": (I, [P, P, I, I, I, I, P]),
     "hd_add": (I, [P, P, P, P, LL, P]),
     "hd_colsum": (I, [P, P, LL, I, I, P]),

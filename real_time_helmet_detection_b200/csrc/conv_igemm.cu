@@ -57,6 +57,15 @@ struct ConvParams {
     const float* ep_scale; const float* ep_shift; int ep_relu;
     int dbg;                  // profiling only (hd_set_conv_debug): 1 = epilogue drains TMEM but skips math/stores,
                               // 2 = MMA issue skipped (halo kernel only)
+    // optional BatchNorm-BACKWARD statistics of the tensor this launch writes (transposed halo kernel only,
+    // hd_conv2d_igemm_bwdstat): the dgrad of a Residual's second conv produces dZ1, whose consumer is the backward of
+    // conv1's BN + ReLU; with g = bf16(out) * (bwd_y * bwd_sc + bwd_sh > 0) the epilogue adds sum g to stat_sum and
+    // sum g * bwd_y to stat_sqsum (raw moments, as bn_bwd_reduce_kernel) and the last CTA turns them into the apply
+    // kernel's coefficients + dgamma / dbeta (bf_*), re-zeroing the sums: the separate reduction pass over dZ1 and Y1
+    // (2 x 134 MB at 128x128, B = 32) becomes one extra read of Y1 under the tensor-bound MMA loop
+    const __nv_bfloat16* bwd_y; const float* bwd_sc; const float* bwd_sh;
+    const float* bf_gamma; const float* bf_mean; const float* bf_rstd; float* bf_coef; float* bf_dgamma; float* bf_dbeta;
+    float bf_count;
     int x2_chunks;            // N=64 halo kernel only: 64-channel chunks of a SECOND input that enters as one extra 1x1
                               // tap (out += W2 * x2): the 1x1 skip-branch dgrad fused into the 3x3 dgrad of a Residual
 };
@@ -184,13 +193,29 @@ __device__ __forceinline__ void flush_stats(const ConvParams& p, float* s_stat, 
         atomicAdd(p.stat_sum + t, s_stat[t]);
         atomicAdd(p.stat_sqsum + t, s_stat[BLOCK_N + t]);
     }
-    if (p.bn_out == nullptr) return;
+    if (p.bn_out == nullptr && p.bf_coef == nullptr) return;
     __threadfence();
     named_bar_sync(1, nthr);
     if (t == 0) *s_flag = (atomicAdd(p.bn_counter, 1u) == gridDim.x - 1) ? 1 : 0;
     named_bar_sync(1, nthr);
     if (*s_flag == 0) return;
     __threadfence();
+    if (p.bf_coef != nullptr) {      // BN-backward statistics (see ConvParams::bwd_y): coefficients of dy = a*g + b*y + c
+        if (t < p.cout) {
+            const float S0 = __ldcg(p.stat_sum + t);
+            const float g = p.bf_gamma[t], r = p.bf_rstd[t], m = p.bf_mean[t];
+            const float S1 = r * (__ldcg(p.stat_sqsum + t) - m * S0);
+            p.bf_coef[t] = g * r;
+            p.bf_coef[p.cout + t] = -g * r * r * S1 / p.bf_count;
+            p.bf_coef[2 * p.cout + t] = g * r * (m * r * S1 - S0) / p.bf_count;
+            if (p.bf_dgamma) p.bf_dgamma[t] = S1;
+            if (p.bf_dbeta) p.bf_dbeta[t] = S0;
+            p.stat_sum[t] = 0.f;            // accumulators left zeroed for the next reduction on this scratch block
+            p.stat_sqsum[t] = 0.f;
+        }
+        if (t == 0) *p.bn_counter = 0u;
+        return;
+    }
     if (t < p.cout) {
         const float sum = __ldcg(p.stat_sum + t), sq = __ldcg(p.stat_sqsum + t);
         const float mean = sum / p.bn_count;
@@ -441,37 +466,48 @@ constexpr int kHaloThreads = 384;
 //     also clips at the image border) instead of LDS + STG.
 // What remains between 92 and ~106 us is the epilogue's TMEM read (128 KB of fp32 accumulators per tile at 64 B/clk
 // = 2048 of the tile's 9216 MMA cycles), which the tensor core's own accumulator traffic has to share.
+// Packed bf16x2 words of a second NHWC tensor of the output's shape (the residual addend, or the consumer's BN input in
+// BN-backward-statistics mode) for one 32-channel x 32-pixel block: lane pair (2m, 2m+1) reads channels (c, c+1) of
+// pixel 2j (even lane) / 2j+1 (odd lane). Issued right after the block's TMEM load, in front of the math. (Requesting
+// them one block AHEAD - before the wait for the accumulator and before the previous block's math, epilogue loop fully
+// unrolled - was measured SLOWER: 137 -> 163 us for the statistics dgrad, 131 -> 137 us for the addend dgrad at 128x128.)
+__device__ __forceinline__ void load_aux_block(const __nv_bfloat16* __restrict__ aux, const ConvParams& p, int cbase,
+                                               uint32_t lane, int n, int x0, int yb, uint32_t (&w)[16]) {
+    const int cpair = cbase + static_cast<int>(lane & ~1u);
+    const size_t row0 = (static_cast<size_t>(n) * p.H + yb) * p.W;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int x = x0 + ((2 * j) & 15) + static_cast<int>(lane & 1u);
+        w[j] = 0u;
+        if (yb + (j >> 3) < p.H && x < p.W)
+            w[j] = __ldg(reinterpret_cast<const uint32_t*>(aux + (row0 + (j >> 3) * p.W + x) * p.out_cs + cpair));
+    }
+}
+
+template <bool BWD>
 __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUtensorMap* tmap_o, uint32_t taddr, int cbase,
                                                  uint32_t lane, int n, int x0, int yb, uint8_t* stage, float bias,
-                                                 float ep_scale, float ep_shift, bool do_stats, float& s1, float& s2) {
+                                                 float ep_scale, float ep_shift, bool do_stats, float& s1, float& s2,
+                                                 const __nv_bfloat16* __restrict__ aux_ptr, float bsc = 0.f, float bsh = 0.f) {
     uint32_t r[32];
     tmem_ld_x32(taddr, r);
+    constexpr bool bwd = BWD;       // BN-backward-statistics instance (never with an addend): see ConvParams::bwd_y
+    uint32_t aux[16];
+    if (aux_ptr) load_aux_block(aux_ptr, p, cbase, lane, n, x0, yb, aux);
     // Lane pair (2m, 2m+1) = channels (c, c+1). For the pixel pair (2j, 2j+1) the even lane ends up with both channels
     // of pixel 2j and the odd lane with both channels of pixel 2j+1 (one shuffle), i.e. one packed bf16x2 word each.
     const uint32_t odd = lane & 1u;
-    uint32_t add[16];
-    if (p.addend) {
-        const int cpair = cbase + static_cast<int>(lane & ~1u);
-        const size_t row0 = (static_cast<size_t>(n) * p.H + yb) * p.W;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int x = x0 + ((2 * j) & 15) + static_cast<int>(odd);
-            add[j] = 0u;
-            if (yb + (j >> 3) < p.H && x < p.W)
-                add[j] = __ldg(reinterpret_cast<const uint32_t*>(p.addend + (row0 + (j >> 3) * p.W + x) * p.out_cs + cpair));
-        }
-    }
     tmem_ld_wait();
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]) + bias, ep_scale, ep_shift);
-    if (p.addend) {
+    if (!BWD && p.addend) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, add[j], 1);
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, aux[j], 1);
             // even lane (channel c): c @ pixel 2j = low half of its own word, c @ 2j+1 = low half of the partner's;
             // odd lane (channel c+1): @ 2j = high half of the partner's word, @ 2j+1 = high half of its own
-            const uint32_t w0 = odd ? other : add[j], w1 = odd ? add[j] : other;
+            const uint32_t w0 = odd ? other : aux[j], w1 = odd ? aux[j] : other;
             v[2 * j] += __uint_as_float(odd ? (w0 & 0xffff0000u) : (w0 << 16));
             v[2 * j + 1] += __uint_as_float(odd ? (w1 & 0xffff0000u) : (w1 << 16));
         }
@@ -497,7 +533,24 @@ __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUte
         tma_store_4d(tmap_o, stage, cbase, x0, yb, n);     // clipped at the image border by the TMA unit
         bulk_commit_group();
     }
-    if (do_stats) {
+    if (bwd) {
+        // g = the STORED (bf16-rounded) value where the consumer's ReLU was open; out-of-image pixels contribute nothing
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, aux[j], 1);
+            const uint32_t w0 = odd ? other : aux[j], w1 = odd ? aux[j] : other;      // as the addend exchange above
+            const float y0 = __uint_as_float(odd ? (w0 & 0xffff0000u) : (w0 << 16));
+            const float y1 = __uint_as_float(odd ? (w1 & 0xffff0000u) : (w1 << 16));
+            const bool row_ok = yb + (j >> 3) < p.H;
+            const int xa = x0 + ((2 * j) & 15);
+            const float g0 = __bfloat162float(__float2bfloat16_rn(v[2 * j]));
+            const float g1 = __bfloat162float(__float2bfloat16_rn(v[2 * j + 1]));
+            const float t0 = (row_ok && xa < p.W && fmaf(y0, bsc, bsh) > 0.f) ? g0 : 0.f;
+            const float t1 = (row_ok && xa + 1 < p.W && fmaf(y1, bsc, bsh) > 0.f) ? g1 : 0.f;
+            s1 += t0 + t1;
+            s2 = fmaf(t0, y0, fmaf(t1, y1, s2));
+        }
+    } else if (do_stats) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const bool ok = (yb + (i >> 4) < p.H) && (x0 + (i & 15) < p.W);
@@ -508,6 +561,7 @@ __device__ __forceinline__ void epilogue_block_t(const ConvParams& p, const CUte
     }
 }
 
+template <bool BWD>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
@@ -620,6 +674,8 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const bool do_stats = p.stat_sum != nullptr;
         const float bias = (p.bias && ch < p.cout) ? __ldg(p.bias + ch) : 0.f;
         const float ep_scale = p.ep_scale ? __ldg(p.ep_scale + ch) : 1.f, ep_shift = p.ep_scale ? __ldg(p.ep_shift + ch) : 0.f;
+        const float bsc = BWD ? __ldg(p.bwd_sc + ch) : 0.f, bsh = BWD ? __ldg(p.bwd_sh + ch) : 0.f;
+        const __nv_bfloat16* aux = BWD ? p.bwd_y : p.addend;
         uint8_t* stage = s_stage + (warp - 4) * 2048;
         float s1 = 0.f, s2 = 0.f;
         uint32_t it = 0;
@@ -634,8 +690,8 @@ conv_igemm_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             if (p.dbg != 1) {
 #pragma unroll 1
                 for (int b = 0; b < 4; ++b)
-                    epilogue_block_t(p, &tmap_o, taddr + b * 32, cbase, lane, n, tx * 16, ty * 16 + 8 * h + 2 * b, stage,
-                                     bias, ep_scale, ep_shift, do_stats, s1, s2);
+                    epilogue_block_t<BWD>(p, &tmap_o, taddr + b * 32, cbase, lane, n, tx * 16, ty * 16 + 8 * h + 2 * b, stage,
+                                     bias, ep_scale, ep_shift, do_stats, s1, s2, aux, bsc, bsh);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -907,7 +963,8 @@ static thread_local int g_conv_variant = 0;  // 0 auto, 1 generic only, 2 halo w
 
 static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
     constexpr int smem_bytes = kHAStages * kHABytes + kHBStages * kHBBytes + 1024 + 256 + 2 * 128 * 4 + 128 + 8 * 2048;
-    HD_ENSURE_DYN_SMEM(conv_igemm_halo_kernel, smem_bytes);
+    HD_ENSURE_DYN_SMEM(conv_igemm_halo_kernel<false>, smem_bytes);
+    HD_ENSURE_DYN_SMEM(conv_igemm_halo_kernel<true>, smem_bytes);
     // store box of the transposed epilogue: 32 channels x 16 columns x 2 rows, dense (un-swizzled) in shared memory
     alignas(64) CUtensorMap to;
     uint64_t dims[4] = {(uint64_t)p.cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
@@ -916,9 +973,13 @@ static int launch_conv_halo(const CUtensorMap& tx, const CUtensorMap& tw, const 
     int rc = make_tmap_bf16(&to, p.out, 4, dims, str, box, /*swizzle_bytes=*/0);
     if (rc) return rc;
     int grid = p.num_tiles < sm_budget() ? p.num_tiles : sm_budget();
-    HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel, grid, kHaloThreads, smem_bytes,
-                                     stream, tx, tw,
-                                     to, p));
+    if (p.bwd_y)
+        HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel<true>, grid, kHaloThreads,
+                                         smem_bytes, stream, tx, tw, to, p));
+    else
+        HD_CHECK_CUDA(::hd::launch_k_pdl(p.num_tiles < sm_count(), conv_igemm_halo_kernel<false>, grid, kHaloThreads,
+                                         smem_bytes, stream, tx, tw,
+                                         to, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -952,7 +1013,36 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
                          cudaStream_t stream, int vtaps = 0, int pad_top = 0, const void* x2 = nullptr,
-                         const void* w2_packed = nullptr, int cin2 = 0);
+                         const void* w2_packed = nullptr, int cin2 = 0, const void* bwd_y = nullptr,
+                         const float* bwd_sc = nullptr, const float* bwd_sh = nullptr, const hd_bn_bwd_fuse* bwd_fin = nullptr);
+
+static bool halo_eligible(int N, int H, int W, int cout, int block_n, int ksize) {
+    using namespace hd;
+    if (!((ksize == 3 || ksize == 1) && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && g_conv_variant != 1)) return false;
+    const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
+    return g_conv_variant == 2 || ht >= sm_count();
+}
+
+// 1 when a (ksize x ksize, cout-channel NHWC bf16) convolution of this shape runs on the transposed halo kernel - the one
+// that can also produce the consumer's BN-backward statistics (hd_conv2d_igemm_bwdstat).
+extern "C" int hd_conv2d_igemm_halo_eligible(int N, int H, int W, int cout, int ksize) {
+    return halo_eligible(N, H, W, cout, cout > 64 ? 128 : 64, ksize) ? 1 : 0;
+}
+
+// See include/hd_b200.h.
+extern "C" int hd_conv2d_igemm_bwdstat(const void* x, const void* w_packed, void* out, int N, int H, int W, int cin, int cout,
+                                       int ksize, const void* y, const float* act_scale, const float* act_shift,
+                                       float* sums, const hd_bn_bwd_fuse* fin, cudaStream_t stream) {
+    using namespace hd;
+    HD_REQUIRE(y && act_scale && act_shift && sums, "conv_igemm_bwdstat: null argument");
+    HD_REQUIRE(fin && fin->coef && fin->counter && fin->gamma && fin->mean && fin->rstd && fin->count > 0.f,
+               "conv_igemm_bwdstat: incomplete finalize block");
+    HD_REQUIRE(halo_eligible(N, H, W, cout, 128, ksize),
+               "conv_igemm_bwdstat: shape (%d,%d,%d) cout %d k %d does not run on the halo kernel (hd_conv2d_igemm_halo_eligible)",
+               N, H, W, cout, ksize);
+    return conv_dispatch(x, w_packed, out, nullptr, nullptr, nullptr, sums, sums + cout, N, H, W, cin, cout, 128, ksize, 0, cout,
+                         0, 0, 1, nullptr, nullptr, nullptr, 0, stream, 0, 0, nullptr, nullptr, 0, y, act_scale, act_shift, fin);
+}
 
 // See include/hd_b200.h for the contract.
 extern "C" int hd_conv2d_igemm(const void* x, const void* w_packed, void* out, void* out2, const float* bias,
@@ -1003,7 +1093,8 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
                          const void* addend, float* stat_sum, float* stat_sqsum, int N, int H, int W, int cin, int cout,
                          int block_n, int ksize, int out_mode, int out_cs, int out2_cs, int stack_idx, int num_stack,
                          const hd_bn_fuse* bn, const float* ep_scale, const float* ep_shift, int ep_relu,
-                         cudaStream_t stream, int vtaps, int pad_top, const void* x2, const void* w2_packed, int cin2) {
+                         cudaStream_t stream, int vtaps, int pad_top, const void* x2, const void* w2_packed, int cin2,
+                         const void* bwd_y, const float* bwd_sc, const float* bwd_sh, const hd_bn_bwd_fuse* bwd_fin) {
     using namespace hd;
     HD_REQUIRE(bn == nullptr || (stat_sum != nullptr && bn->out && bn->counter && bn->gamma && bn->beta),
                "conv_igemm: fused BN finalize needs statistics, gamma/beta, an output block and a ticket counter");
@@ -1048,16 +1139,19 @@ static int conv_dispatch(const void* x, const void* w_packed, void* out, void* o
 
     // halo kernel: 3x3 (or 1x1: same kernel, one tap, no halo rows), 128 output channels, map >= 16x16 and enough 16x16
     // tiles to fill the machine
-    bool halo = false;
-    if ((ksize == 3 || ksize == 1) && vtaps == 0 && block_n == 128 && cout == 128 && H >= 16 && W >= 16 && out_mode == 0 &&
-        g_conv_variant != 1) {
-        const int ht = ((W + 15) / 16) * ((H + 15) / 16) * N;
-        halo = g_conv_variant == 2 || ht >= sm_count();
-        if (halo) {
-            tw = 16; th = 16 + 2 * p.pad; tn = 1;       // activation box: 16x16 pixels plus the 3x3 halo rows
-            p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
-            p.num_tiles = ht;
-        }
+    const bool halo = vtaps == 0 && out_mode == 0 && halo_eligible(N, H, W, cout, block_n, ksize);
+    if (halo) {
+        tw = 16; th = 16 + 2 * p.pad; tn = 1;       // activation box: 16x16 pixels plus the 3x3 halo rows
+        p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16; p.tiles_n = N;
+        p.num_tiles = ((W + 15) / 16) * ((H + 15) / 16) * N;
+    }
+    if (bwd_y) {
+        HD_REQUIRE(halo && bwd_fin && addend == nullptr && bn == nullptr && ep_scale == nullptr && out_cs == cout,
+                   "conv_igemm: BN-backward statistics need the halo kernel, a dense output and no other epilogue option");
+        p.bwd_y = reinterpret_cast<const __nv_bfloat16*>(bwd_y); p.bwd_sc = bwd_sc; p.bwd_sh = bwd_sh;
+        p.bf_gamma = bwd_fin->gamma; p.bf_mean = bwd_fin->mean; p.bf_rstd = bwd_fin->rstd; p.bf_coef = bwd_fin->coef;
+        p.bf_dgamma = bwd_fin->dgamma; p.bf_dbeta = bwd_fin->dbeta; p.bf_count = bwd_fin->count;
+        p.bn_counter = bwd_fin->counter;
     }
     // N=64 halo kernel: 64 output channels on a map with enough 16x16 tiles to fill the machine (the 256x256 level)
     bool n64 = false;

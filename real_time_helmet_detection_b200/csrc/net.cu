@@ -659,29 +659,51 @@ static void dgrad_unit(hd_net* n, int ui, const bf16* dy, bf16* dx, int B, int H
 // BN (+ReLU) backward of one unit: g = dout * (out > 0) -> dy (and the skip branch / g when requested)
 // pool_idx != nullptr: `dout` is the gradient of the 2x2-POOLED block output and pool_idx the argmax the fused forward
 // tail stored (two-branch tails only): the BN-backward kernels route it themselves (hd_bn_bwd_*_pool)
-static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, const bf16* y, bf16* dy, int us,
-                        const bf16* ys, bf16* dys, bf16* gout, const uint8_t* mask = nullptr,
-                        const uint8_t* pool_idx = nullptr, int pB = 0, int pH = 0, int pW = 0) {
+// The "last CTA finalizes" block of unit ui's BN backward on the CURRENT lane's scratch (n->small: sums [3][256] |
+// coef [3][256] | coef_s [3][256] | ticket, epoch). `sums` and the ticket are zeroed once per forward pass and re-zeroed
+// by every fused finalize after use.
+static hd_bn_bwd_fuse bn_bwd_fin(hd_net* n, int ui, int us) {
     Unit& u = n->units[ui];
     const hd_unit_ptrs& p = UP(n, ui);
+    const int C = u.cout;
+    hd_bn_bwd_fuse fin{};
+    fin.gamma = p.gamma; fin.mean = u.bnp + 2 * C; fin.rstd = u.bnp + 3 * C; fin.coef = n->small + 3 * 256;
+    fin.dgamma = p.dgamma; fin.dbeta = p.dbeta;
+    fin.count = static_cast<float>(u.npix);
+    fin.counter = reinterpret_cast<unsigned int*>(n->small + 9 * 256);
+    if (us >= 0) {
+        const Unit& s = n->units[us];
+        const hd_unit_ptrs& ps = UP(n, us);
+        fin.gamma_s = ps.gamma; fin.mean_s = s.bnp + 2 * C; fin.rstd_s = s.bnp + 3 * C; fin.coef_s = n->small + 6 * 256;
+        fin.dgamma_s = ps.dgamma; fin.dbeta_s = ps.dbeta;
+    }
+    return fin;
+}
+
+// maps up to this many pixels take the one-launch BN backward (bn_bwd_fused_small_kernel)
+static long long bn_fused_small_max() {
+    static const long long v = getenv("HD_BN_FUSED_SMALL_MAX") ? atoll(getenv("HD_BN_FUSED_SMALL_MAX")) : 32768;
+    return v;
+}
+
+// presummed: the producer of `dout` (hd_conv2d_igemm_bwdstat) has already left this BN's coefficients and dgamma / dbeta
+// in the lane's scratch - only the apply pass remains (plain conv + BN + ReLU units)
+static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, const bf16* y, bf16* dy, int us,
+                        const bf16* ys, bf16* dys, bf16* gout, const uint8_t* mask = nullptr,
+                        const uint8_t* pool_idx = nullptr, int pB = 0, int pH = 0, int pW = 0, bool presummed = false) {
+    Unit& u = n->units[ui];
     const int C = u.cout;
     float* sums = n->small;            // [3][C]
     float* coef = n->small + 3 * 256;  // [3][C]
     float* coef_s = n->small + 6 * 256;
-    // `sums` and the ticket counter are zeroed once per forward pass and re-zeroed by the fused finalize after use
-    const float* mean = u.bnp + 2 * C;
-    const float* rstd = u.bnp + 3 * C;
     const Unit* s = us >= 0 ? &n->units[us] : nullptr;
     // out == nullptr: plain conv+BN+ReLU unit, the mask is recomputed from y and this unit's scale/shift.
     // The reduction's last block also produces the coefficients and dgamma / dbeta (no separate finalize launch).
-    hd_bn_bwd_fuse fin{};
-    fin.gamma = p.gamma; fin.mean = mean; fin.rstd = rstd; fin.coef = coef; fin.dgamma = p.dgamma; fin.dbeta = p.dbeta;
-    fin.count = static_cast<float>(u.npix);
-    fin.counter = reinterpret_cast<unsigned int*>(n->small + 9 * 256);
-    if (s) {
-        const hd_unit_ptrs& ps = UP(n, us);
-        fin.gamma_s = ps.gamma; fin.mean_s = s->bnp + 2 * C; fin.rstd_s = s->bnp + 3 * C; fin.coef_s = coef_s;
-        fin.dgamma_s = ps.dgamma; fin.dbeta_s = ps.dbeta;
+    hd_bn_bwd_fuse fin = bn_bwd_fin(n, ui, us);
+    if (presummed) {
+        RUN(hd_bn_bwd_apply(dout, nullptr, u.bnp, u.bnp + C, nullptr, nullptr, y, coef, dy, nullptr, nullptr, nullptr, nullptr,
+                            u.npix, C, n->stream));
+        return;
     }
     // two-branch tail (skip conv + BN): the ReLU mask is rebuilt from the two conv outputs the kernels read anyway
     // instead of reading the stored block output (saves a 537 MB read per kernel at 256x256)
@@ -695,7 +717,7 @@ static void bn_bwd_unit(hd_net* n, int ui, const bf16* dout, const bf16* out, co
         return;
     }
     // small maps (the deep hourglass levels): one launch instead of two, see bn_bwd_fused_small_kernel
-    static const long long fused_max = getenv("HD_BN_FUSED_SMALL_MAX") ? atoll(getenv("HD_BN_FUSED_SMALL_MAX")) : 32768;
+    const long long fused_max = bn_fused_small_max();
     unsigned int* epoch = reinterpret_cast<unsigned int*>(n->small + 9 * 256) + 1;
     if (!s && u.npix <= fused_max && (mask || out == nullptr)) {
         RUN(hd_bn_bwd_fused_small(dout, mask, mask ? nullptr : u.bnp, mask ? nullptr : u.bnp + C, y, sums, dy,
@@ -725,14 +747,32 @@ static void residual_bwd(hd_net* n, int ri, const bf16* dOut, bf16* dX, int B, c
     bf16* G = r.us >= 0 ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
     bn_bwd_unit(n, r.u2, dOut, r.Out, r.Y2, dY2, r.us, r.Ys, dYs, G, r.Mask, pool_idx, B, H, W);
     bf16* dZ1 = reinterpret_cast<bf16*>(n->bw.alloc(bytes_o));
-    dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
+    // HD_DGRAD_BNSTAT=1 (opt-in, read per call so that one process can compare both): conv2's dgrad also reduces the
+    // statistics of conv1's BN backward in its epilogue when it runs on the halo kernel (maps >= 16x16 with enough tiles)
+    // and the map is too large for the one-launch BN backward; the reduction pass over dZ1 and Y1 disappears (-1.6 GB of
+    // DRAM traffic per step, -0.32 ms of serialised kernel time). MEASURED NEUTRAL on the step (same box, graph replay:
+    // 11.97 / 11.82 ms without, 11.76 / 11.90 with): the dgrad gets 25 us longer at 128x128 (112 -> 137 us; 427 -> 516 at
+    // 256x256) and, unlike the HBM-bound reduction it replaces, a persistent tensor-core kernel cannot share the SMs with
+    // the weight-gradient stream - the work moved from a kernel that overlapped into one that does not.
+    const char* bnstat_env = getenv("HD_DGRAD_BNSTAT");
+    Unit& uc2 = n->units[r.u2];
+    const bool bnstat = bnstat_env != nullptr && bnstat_env[0] == '1' && uc2.cin == 128 && uc2.cout == 128 && n->units[r.u1].npix > bn_fused_small_max() &&
+                        hd_conv2d_igemm_halo_eligible(B, H, W, 128, uc2.k) == 1;
+    if (bnstat) {
+        Unit& uc1 = n->units[r.u1];
+        hd_bn_bwd_fuse fin = bn_bwd_fin(n, r.u1, -1);
+        RUN(hd_conv2d_igemm_bwdstat(dY2, uc2.wpd, dZ1, B, H, W, pad64(uc2.cout), uc2.cin, uc2.k, r.Y1, uc1.bnp, uc1.bnp + uc1.cout,
+                                    n->small, &fin, n->stream));
+    } else {
+        dgrad_unit(n, r.u2, dY2, dZ1, B, H, W, nullptr);
+    }
     // The readiness event is recorded AFTER the dgrad launch on purpose: dgrad and wgrad are both persistent
     // tensor-core kernels that cannot share an SM, so the wgrad should start when the dgrad ends - exactly when the
     // HBM-bound BN-backward kernels below start on the main stream and can co-run with it.
     cudaEvent_t e2 = mark_ready(n);
     wgrad_unit(n, r.u2, r.Z1, dY2, B, H, W, e2);
     if (r.us >= 0) wgrad_unit(n, r.us, r.X, dYs, B, H, W, e2);
-    bn_bwd_unit(n, r.u1, dZ1, nullptr, r.Y1, dY1, -1, nullptr, nullptr, nullptr);
+    bn_bwd_unit(n, r.u1, dZ1, nullptr, r.Y1, dY1, -1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, bnstat);
     if (r.us < 0) {
         dgrad_unit(n, r.u1, dY1, dX, B, H, W, G);
     } else {

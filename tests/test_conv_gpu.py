@@ -280,3 +280,56 @@ def test_conv_n64_dual_input_is_fused_residual_dgrad(cuda_device, force_halo, N,
     out = ops.to_nchw(ops.conv2d_igemm_dual(ops.to_nhwc(dy1.to(cuda_device)), w1d, ops.to_nhwc(dys.to(cuda_device)), wsd,
                                             64, 3)).cpu()
     assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() and _rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("N,H,W,k", [(2, 32, 32, 3), (1, 40, 24, 3), (3, 17, 33, 3), (2, 16, 48, 1), (32, 64, 64, 3)])
+def test_conv_dgrad_with_bn_backward_statistics(cuda_device, force_halo, N, H, W, k):
+    """hd_conv2d_igemm_bwdstat: the halo kernel's output is bit-identical to the plain launch, and the BN-backward
+    coefficients / dgamma / dbeta its last CTA leaves equal hd_bn_bwd_reduce_fin's on that output (ragged maps: pixels
+    outside the image must not count); the scratch (sums, ticket) is left zeroed, twice in a row."""
+    import ctypes
+    from real_time_helmet_detection_b200 import ops, _lib
+
+    class Fuse(ctypes.Structure):
+        _fields_ = [(n_, ctypes.c_void_p) for n_ in ("gamma", "mean", "rstd", "coef", "dgamma", "dbeta", "gamma_s", "mean_s",
+                                                     "rstd_s", "coef_s", "dgamma_s", "dbeta_s")] + \
+                   [("count", ctypes.c_float), ("counter", ctypes.c_void_p)]
+
+    C = 128
+    d = cuda_device
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5 + H + W + k)
+    dy2 = ops.to_nhwc(_bf16_round(torch.randn(N, C, H, W, generator=g)).to(d))
+    y1 = ops.to_nhwc(_bf16_round(torch.randn(N, C, H, W, generator=g)).to(d))
+    w = _bf16_round(torch.randn(C, C, k, k, generator=g) * (1.0 / (C * k * k) ** 0.5)).to(d)
+    wpd = ops.pack_weight(w, mode=1)
+    bnp = torch.stack([torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5, torch.randn(C, generator=g) * 0.1,
+                       torch.rand(C, generator=g) + 0.5]).to(d)                     # scale | shift | mean | rstd
+    gamma = (torch.rand(C, generator=g) + 0.5).to(d)
+    npix = N * H * W
+    assert L.hd_conv2d_igemm_halo_eligible(N, H, W, C, k) == 1
+    plain = ops.conv2d_igemm(dy2, wpd, C, k)
+
+    def scratch():
+        s = torch.zeros(16 * 256, device=d)
+        outs = [torch.empty(C, device=d) for _ in range(2)]
+        f = Fuse()
+        f.gamma, f.mean, f.rstd = gamma.data_ptr(), bnp[2].data_ptr(), bnp[3].data_ptr()
+        f.coef, f.dgamma, f.dbeta = s[768:].data_ptr(), outs[0].data_ptr(), outs[1].data_ptr()
+        f.count, f.counter = float(npix), s[9 * 256:].data_ptr()
+        return s, outs, f
+
+    sA, outsA, fA = scratch()
+    _lib.check(L.hd_bn_bwd_reduce_fin(_lib.ptr(plain), None, _lib.ptr(bnp[0]), _lib.ptr(bnp[1]), None, None, _lib.ptr(y1), None,
+                                      _lib.ptr(sA), npix, C, ctypes.byref(fA), _lib.stream()))
+    sB, outsB, fB = scratch()
+    for rep in range(2):
+        out = torch.empty_like(plain)
+        _lib.check(L.hd_conv2d_igemm_bwdstat(_lib.ptr(dy2), _lib.ptr(wpd), _lib.ptr(out), N, H, W, C, C, k, _lib.ptr(y1),
+                                             _lib.ptr(bnp[0]), _lib.ptr(bnp[1]), _lib.ptr(sB), ctypes.byref(fB), _lib.stream()))
+        assert torch.equal(out, plain)
+        for a, b in zip(outsA, outsB):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-4 * float(a.abs().max()) + 1e-5), float((a - b).abs().max())
+        assert torch.allclose(sA[768:768 + 3 * C], sB[768:768 + 3 * C], rtol=1e-4, atol=1e-6)
+        torch.cuda.synchronize()
+        assert float(sB[:768].abs().max()) == 0.0 and int(sB[9 * 256:].view(torch.int32)[0]) == 0

@@ -36,6 +36,8 @@ struct WgradParams {
     int tiles_x, tiles_y, num_tiles;
     float* ws;                 // [ksplit][taps][128][BLOCK_N]
     int taps;
+    int hx0, hy0;              // halo variants: box origin relative to the pixel tile (3x3: -1, -1 + the CTA's dx group;
+                               // space-to-depth stem, four vertical taps in ONE 11-row box: 0, -2)
     // in-kernel split-K reduction (replaces the separate wgrad_reduce launch): after a grid-wide barrier on sync[0]
     // every CTA sums its slice of the partials straight into the OIHW gradient
     float* grad;
@@ -47,12 +49,16 @@ struct WgradParams {
 // pixel tile is then ONE box of (8+2) rows x 16 columns at the dx-shifted x coordinate, and the three dy taps are
 // the same shared-memory tile read at a row offset of dy*16 pixels = dy*2048 bytes (a whole number of 8-row swizzle
 // groups, so the UMMA descriptor just starts later). X traffic per tile drops from 3 x 32 KB to 40 KB.
-template <int BLOCK_N, bool HALO>
+// HROWS = pixel rows x 16 of that box: 0 (no halo: one box per tap), 160 (3x3: 8 + 2 rows), 176 (the stem's column of four
+// vertical taps, 8 + 3 rows: its X operand was fetched four times per tile - 1.3 GB of L2 -> SM traffic per launch at
+// 256x256, B = 32, which is what paced the kernel - and is now fetched once).
+template <int BLOCK_N, int HROWS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
     pdl_launch_dependents();
-    constexpr int kBRows = HALO ? 160 : 128;
+    constexpr bool HALO = HROWS != 0;
+    constexpr int kBRows = HALO ? HROWS : 128;
     constexpr int kBBytes = kBRows * BLOCK_N * 2;
     constexpr int kNChunks = BLOCK_N / 64;
     constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
@@ -120,7 +126,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 #pragma unroll
                     for (int c = 0; c < kNChunks; ++c)
                         tma_load_4d(smem_b + stage * kBBytes + c * kBRows * 128, &tmap_x, &full_bar[stage], c * 64,
-                                    x0 + group - 1, y0 - 1, n0);
+                                    x0 + group + p.hx0, y0 + p.hy0, n0);
                     if (++stage == kWgBStages) { stage = 0; phase ^= 1; }
                 } else {
                     for (int t = 0; t < p.taps_per_group; ++t) {
@@ -151,8 +157,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                     const uint32_t sb = smem_u32(smem_b + stage * kBBytes);
                     const uint64_t adesc = umma_smem_desc_sw128(sa, 128 * 128, 1024);
                     const uint64_t bdesc = umma_smem_desc_sw128(sb, kBRows * 128, 1024);
+                    constexpr int kTapsHalo = HROWS == 176 ? 4 : 3;
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
+                    for (int t = 0; t < kTapsHalo; ++t) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             umma_bf16(tmem_base + t * BLOCK_N, adesc + 128 * k, bdesc + 128 * (k + t), kIdesc,
@@ -332,12 +339,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     *g = accumulate ? (*g + s) : s;
 }
 
-template <int BLOCK_N, bool HALO>
+template <int BLOCK_N, int HROWS>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
-    constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
-    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HALO ? 160 : 128) * BLOCK_N * 2 + 1024 + 256 + 4 * 4096;
-    HD_ENSURE_DYN_SMEM((conv_wgrad_kernel<BLOCK_N, HALO>), smem_bytes);
-    HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HALO>,
+    constexpr int kWgBStages = (BLOCK_N > 128 || HROWS != 0) ? 3 : 4;
+    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HROWS != 0 ? HROWS : 128) * BLOCK_N * 2 + 1024 + 256 + 4 * 4096;
+    HD_ENSURE_DYN_SMEM((conv_wgrad_kernel<BLOCK_N, HROWS>), smem_bytes);
+    HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HROWS>,
                                      p.groups * p.ksplit,
                                      kWgThreads, smem_bytes, stream, tdy, tx, p));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
@@ -429,6 +436,9 @@ extern "C" int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w
     static const bool fused = getenv("HD_WGRAD_FUSED_REDUCE") != nullptr;
     p.sync = fused ? sync_words : nullptr;
     const bool halo = ksize == 3 && tw == 16 && th == 8;   // the dy taps become row offsets of one 10-row X tile
+    static const bool no_stem_halo = getenv("HD_NO_STEM_WGRAD_HALO") != nullptr;
+    const bool halo4 = stem_perm == 2 && tw == 16 && th == 8 && !no_stem_halo;   // four vertical taps: one 11-row X tile
+    p.hx0 = halo4 ? 0 : -1; p.hy0 = halo4 ? -2 : -1;
 
     alignas(64) CUtensorMap tdy, tx;
     {
@@ -441,13 +451,14 @@ extern "C" int hd_conv2d_wgrad_sync(const void* x, const void* dy, float* grad_w
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
-        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)(halo ? th + 2 : th), (uint32_t)tn};
+        uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)(halo ? th + 2 : (halo4 ? th + 3 : th)), (uint32_t)tn};
         int rc = make_tmap_bf16(&tx, x, 4, dims, str, box);
         if (rc) return rc;
     }
-    int rc = (cin == 192)   ? launch_wgrad<192, false>(tdy, tx, p, stream)
-             : (cin == 128) ? (halo ? launch_wgrad<128, true>(tdy, tx, p, stream) : launch_wgrad<128, false>(tdy, tx, p, stream))
-                            : (halo ? launch_wgrad<64, true>(tdy, tx, p, stream) : launch_wgrad<64, false>(tdy, tx, p, stream));
+    int rc = (cin == 192)   ? launch_wgrad<192, 0>(tdy, tx, p, stream)
+             : (cin == 128) ? (halo ? launch_wgrad<128, 160>(tdy, tx, p, stream) : launch_wgrad<128, 0>(tdy, tx, p, stream))
+             : halo4        ? launch_wgrad<64, 176>(tdy, tx, p, stream)
+                            : (halo ? launch_wgrad<64, 160>(tdy, tx, p, stream) : launch_wgrad<64, 0>(tdy, tx, p, stream));
     if (rc) return rc;
     if (p.sync == nullptr) {
         const int total = p.taps * cout * cin_real;

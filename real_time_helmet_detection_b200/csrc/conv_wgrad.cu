@@ -24,6 +24,24 @@ namespace hd {
 
 constexpr int kWgThreads = 256;
 constexpr int kWgABytes = 2 * 128 * 128;  // dY tile: 128 pixels x 128 cout (two 64-channel atoms)
+// dY buffers / X ring stages per variant (shared memory: <= 227 KB with the 1 KB alignment slack, barriers and 16 KB of
+// epilogue staging; HD_WGRAD_SHALLOW at build time restores the first version's 2 / 3-4)
+#ifdef HD_WGRAD_SHALLOW
+__host__ __device__ constexpr int wg_a_bufs(int) { return 2; }
+__host__ __device__ constexpr int wg_b_stages(int block_n, int hrows) { return (block_n > 128 || hrows != 0) ? 3 : 4; }
+#else
+__host__ __device__ constexpr int wg_a_bufs(int block_n) { return block_n == 64 ? 3 : 2; }
+__host__ __device__ constexpr int wg_b_stages(int block_n, int hrows) {
+    return block_n == 64 ? (hrows != 0 ? 5 : 6) : ((block_n > 128 || hrows != 0) ? 3 : 4);
+}
+#endif
+__host__ __device__ constexpr int wg_smem_bytes(int block_n, int hrows) {
+    return wg_a_bufs(block_n) * kWgABytes + wg_b_stages(block_n, hrows) * (hrows != 0 ? hrows : 128) * block_n * 2 + 1024 + 256 +
+           4 * 4096;
+}
+static_assert(wg_smem_bytes(64, 0) <= 232448 && wg_smem_bytes(64, 160) <= 232448 && wg_smem_bytes(64, 176) <= 232448 &&
+                  wg_smem_bytes(128, 0) <= 232448 && wg_smem_bytes(128, 160) <= 232448 && wg_smem_bytes(192, 0) <= 232448,
+              "conv_wgrad: shared memory");
 
 struct WgradParams {
     int N, H, W;
@@ -61,19 +79,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     constexpr int kBRows = HALO ? HROWS : 128;
     constexpr int kBBytes = kBRows * BLOCK_N * 2;
     constexpr int kNChunks = BLOCK_N / 64;
-    constexpr int kWgBStages = (BLOCK_N > 128 || HALO) ? 3 : 4;
+    // operand pipeline depth: the 64-input-channel variants (the 256x256 level: K = 2.1 M pixels per launch) were paced
+    // by the ~1.9 us latency of a loaded HBM against two dY tiles in flight; their small X tiles leave room for a third
+    // dY buffer and a deeper X ring
+    constexpr int kABufs = wg_a_bufs(BLOCK_N);
+    constexpr int kWgBStages = wg_b_stages(BLOCK_N, HROWS);
     constexpr uint32_t kIdesc = umma_idesc_bf16(BLOCK_N, 1, 1);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;                       // 2 buffers
-    uint8_t* smem_b = smem + 2 * kWgABytes;       // kWgBStages buffers
+    uint8_t* smem_a = smem;                       // kABufs buffers
+    uint8_t* smem_b = smem + kABufs * kWgABytes;  // kWgBStages buffers
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kWgBStages * kBBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgBStages;
     uint64_t* a_full = bars + 2 * kWgBStages;
-    uint64_t* a_empty = a_full + 2;
-    uint64_t* tmem_full = a_empty + 2;
+    uint64_t* a_empty = a_full + kABufs;
+    uint64_t* tmem_full = a_empty + kABufs;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -93,7 +115,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kABufs; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
         }
@@ -115,7 +137,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                 const int ty = (tile / p.tiles_x) % p.tiles_y;
                 const int tn = tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << p.tn_log2;
-                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                const uint32_t ab = it % kABufs, aphase = (it / kABufs) & 1;
                 mbar_wait(&a_empty[ab], aphase ^ 1);
                 mbar_arrive_expect_tx(&a_full[ab], kWgABytes);
                 tma_load_4d(smem_a + ab * kWgABytes, &tmap_dy, &a_full[ab], 0, x0, y0, n0);
@@ -146,7 +168,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     } else if (warp == 1) {
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = split; tile < p.num_tiles; tile += p.ksplit, ++it) {
-            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t ab = it % kABufs, aphase = (it / kABufs) & 1;
             mbar_wait(&a_full[ab], aphase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem_a + ab * kWgABytes);
@@ -341,8 +363,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 
 template <int BLOCK_N, int HROWS>
 static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, cudaStream_t stream) {
-    constexpr int kWgBStages = (BLOCK_N > 128 || HROWS != 0) ? 3 : 4;
-    constexpr int smem_bytes = 2 * kWgABytes + kWgBStages * (HROWS != 0 ? HROWS : 128) * BLOCK_N * 2 + 1024 + 256 + 4 * 4096;
+    constexpr int smem_bytes = wg_smem_bytes(BLOCK_N, HROWS);
     HD_ENSURE_DYN_SMEM((conv_wgrad_kernel<BLOCK_N, HROWS>), smem_bytes);
     HD_CHECK_CUDA(::hd::launch_k_pdl(p.groups * p.ksplit < sm_count() / 2, conv_wgrad_kernel<BLOCK_N, HROWS>,
                                      p.groups * p.ksplit,

@@ -8,6 +8,9 @@
 #include <cuda_bf16.h>
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "hd_b200.h"
 #include "hd_common.h"
@@ -74,6 +77,46 @@ static inline int grid_for(size_t work, int block, int max_blocks) {
     return (int)g;
 }
 
+// Traversal order and grid of the streaming kernels that sit between two convolutions (round 2, last experiment).
+// A convolution writes its output tiles front to back, so when it ends the TAIL of that tensor is what the 126 MB L2 still
+// holds; a consumer that also walks front to back starts at the evicted head and has displaced the tail by the time it gets
+// there (ncu: these kernels read every byte from DRAM). Walking BACK to front the consumer finds the tail in L2, and what it
+// writes last - the head of its own output - is what the next convolution reads first. That only works if the whole grid
+// sweeps the tensor ONCE: grid = the number of CTAs that are resident at the same time (occupancy x SMs) instead of a
+// fixed 16 per SM (2.7 passes at 128x128, each touching every 2.7th line).
+// MEASURED (same box, graph replay, ms per step): front-to-back 11.91 / 11.86; reversed 11.75; reversed + single sweep
+// 11.84 / 11.85; single sweep alone 11.94. The reuse is real but small (the L2 keeps less of a 134 MB write stream than
+// its size suggests), and the single-sweep grid costs what it gains (fewer CTAs in flight beside a weight-gradient CTA).
+//   HD_EW_REVERSE=0 : front to back (first version)      HD_EW_SWEEP1=1 : one-sweep grids (default: fixed CTAs per SM)
+static bool ew_reverse() {
+    const char* e = getenv("HD_EW_REVERSE");
+    return !(e != nullptr && e[0] == '0');
+}
+static bool ew_sweep1() {
+    const char* e = getenv("HD_EW_SWEEP1");
+    return e != nullptr && e[0] == '1';
+}
+// CTAs of `kernel` (256 threads, `smem` dynamic bytes) resident on the device at once; `fallback` when not sweeping once
+template <typename K>
+static int sweep_grid(K kernel, size_t work_items, int items_per_block, size_t smem, int fallback_per_sm) {
+    int per_sm = fallback_per_sm;
+    if (ew_sweep1()) {
+        static std::mutex mu;
+        static std::map<std::pair<const void*, size_t>, int> cache;     // occupancy per (kernel, dynamic smem)
+        const std::pair<const void*, size_t> key(reinterpret_cast<const void*>(kernel), smem);
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ <= 0)
+                occ = fallback_per_sm;
+            it = cache.emplace(key, occ).first;
+        }
+        per_sm = it->second;
+    }
+    return grid_for(work_items, items_per_block, sm_count() * per_sm);
+}
+
 // ---------------------------------------------------------------------------------------------- BN finalize
 // bnp layout per BN layer (fp32, 6*C): scale | shift | mean | rstd | (unused) | (unused)
 __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, float count,
@@ -111,7 +154,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 // z = act(y * scale + shift)
 template <bool RELU>
 __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                              const float* __restrict__ shift, __nv_bfloat16* __restrict__ z, size_t nvec, int C) {
+                              const float* __restrict__ shift, __nv_bfloat16* __restrict__ z, size_t nvec, int C, int rev) {
     pdl_prologue();
     __shared__ __align__(16) float s_sc[256], s_sh[256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -119,20 +162,23 @@ __global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, const float* 
         s_sh[i] = shift[i];
     }
     __syncthreads();
-    // blockDim (256) is a multiple of C/8, so a thread always works on the same 8 channels
-    const int c0 = static_cast<int>(threadIdx.x % (C >> 3)) << 3;
+    // blockDim (256) is a multiple of C/8, so a thread always works on the same 8 channels (rev: vector nvec-1-i, i.e.
+    // the mirrored channel group - nvec is a multiple of C/8)
+    const int cv = static_cast<int>(threadIdx.x % (C >> 3));
+    const int c0 = (rev ? (C >> 3) - 1 - cv : cv) << 3;
     float sc[8], sh[8];
     lds8(s_sc, c0, sc);
     lds8(s_sh, c0, sh);
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        F8 a = load8(y + i * 8);
+        const size_t e = rev ? nvec - 1 - i : i;
+        F8 a = load8(y + e * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float t = fmaf(a.v[j], sc[j], sh[j]);
             a.v[j] = RELU ? fmaxf(t, 0.f) : t;
         }
-        store8(z + i * 8, a);
+        store8(z + e * 8, a);
     }
 }
 
@@ -141,7 +187,7 @@ template <bool SKIP_BN>
 __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ s2,
                                    const float* __restrict__ b2, const __nv_bfloat16* __restrict__ skip,
                                    const float* __restrict__ ss, const float* __restrict__ bs,
-                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, size_t nvec, int C) {
+                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask, size_t nvec, int C, int rev) {
     pdl_prologue();
     __shared__ __align__(16) float p[4][256];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -151,14 +197,16 @@ __global__ void bn_add_relu_kernel(const __nv_bfloat16* __restrict__ y2, const f
         p[3][i] = SKIP_BN ? bs[i] : 0.f;
     }
     __syncthreads();
-    const int c0 = static_cast<int>(threadIdx.x % (C >> 3)) << 3;
+    const int cv = static_cast<int>(threadIdx.x % (C >> 3));
+    const int c0 = (rev ? (C >> 3) - 1 - cv : cv) << 3;          // see bn_act_kernel
     float k0[8], k1[8], k2[8], k3[8];
     lds8(p[0], c0, k0);
     lds8(p[1], c0, k1);
     lds8(p[2], c0, k2);
     lds8(p[3], c0, k3);
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    for (size_t i0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec;
+         i0 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t i = rev ? nvec - 1 - i0 : i0;
         F8 a = load8(y2 + i * 8);
         F8 k = load8(skip + i * 8);
 #pragma unroll
@@ -323,7 +371,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const float* __restrict__ act_scale_s, const float* __restrict__ act_shift_s,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ ys,
                      float* __restrict__ sums, size_t npix, int C, const hd_bn_bwd_fuse fin,
-                     const uint8_t* __restrict__ mbits) {
+                     const uint8_t* __restrict__ mbits, int rev) {
     pdl_prologue();
     extern __shared__ __align__(16) float red[];  // [3][C]
     const int cvec = C >> 3;
@@ -356,7 +404,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
             uint32_t mm[U];
 #pragma unroll
             for (int h = 0; h < U; ++h) {
-                const size_t o = (pix + h * pstride) * C + c0;
+                const size_t pp = pix + h * pstride;
+                const size_t o = (rev ? npix - 1 - pp : pp) * C + c0;       // back to front: see ew_reverse()
                 rg[h] = ldg16(dout + o);
                 ry[h] = ldg16(y + o);
                 ro[h] = make_uint4(0, 0, 0, 0);
@@ -389,7 +438,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         }
     }
     for (; pix < npix; pix += pstride) {
-        const size_t off = pix * C + c0;
+        const size_t off = (rev ? npix - 1 - pix : pix) * C + c0;
         F8 g = load8(dout + off);
         F8 yy = load8(y + off);
         F8 o, y2;
@@ -1083,11 +1132,11 @@ extern "C" int hd_bn_act(cvp y, const float* scale, const float* shift, void* z,
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (relu)
-        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z),
-                                     nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<true>, sweep_grid(bn_act_kernel<true>, nvec, 256, 0, 16), 256, 0, stream,
+                                     BF(y), scale, shift, BFW(z), nvec, C, ew_reverse() ? 1 : 0));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y), scale, shift, BFW(z),
-                                     nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_act_kernel<false>, sweep_grid(bn_act_kernel<false>, nvec, 256, 0, 16), 256, 0, stream,
+                                     BF(y), scale, shift, BFW(z), nvec, C, ew_reverse() ? 1 : 0));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -1100,11 +1149,11 @@ extern "C" int hd_bn_add_relu_mask(cvp y2, const float* s2, const float* b2, cvp
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
     if (ss)
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2,
-                                     BF(skip), ss, bs, BFW(out), mask, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<true>, sweep_grid(bn_add_relu_kernel<true>, nvec, 256, 0, 16), 256, 0,
+                                     stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C, ew_reverse() ? 1 : 0));
     else
-        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, ew_blocks(nvec), 256, 0, stream, BF(y2), s2, b2,
-                                     BF(skip), ss, bs, BFW(out), mask, nvec, C));
+        HD_CHECK_CUDA(::hd::launch_k(bn_add_relu_kernel<false>, sweep_grid(bn_add_relu_kernel<false>, nvec, 256, 0, 16), 256, 0,
+                                     stream, BF(y2), s2, b2, BF(skip), ss, bs, BFW(out), mask, nvec, C, ew_reverse() ? 1 : 0));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -1176,42 +1225,44 @@ static int bn_bwd_reduce_impl(cvp dout, cvp out, const uint8_t* mbits, const flo
     HD_REQUIRE(mbits == nullptr || ys == nullptr, "bn_bwd_reduce: mask bits are for single-BN tails");
     if (npix == 0) return HD_OK;
     const int rows = 256 / (C / 8);
-    const int blocks = grid_for(static_cast<size_t>(npix), rows * 4, sm_count() * 8);
     const size_t smem = 3 * static_cast<size_t>(C) * sizeof(float);
     const size_t np = static_cast<size_t>(npix);
     const int unroll = bn_bwd_unroll();      // pixels per iteration of the single-BN variants
     const uint8_t* nomask = nullptr;
+    const int rev = ew_reverse() ? 1 : 0;
+    int blocks = grid_for(np, rows * 4, sm_count() * 8);
 #define HD_RED(U_, RM_, OUT_, MB_)                                                                                   \
+    blocks = sweep_grid(bn_bwd_reduce_kernel<false, RM_, U_>, np, rows * 4, smem, 8);                                \
     HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, RM_, U_>, blocks, 256, smem, stream, BF(dout), OUT_, act_scale, \
-                                 act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, MB_))
+                                 act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin, MB_, rev))
     if (unroll > 1 && !ys && mbits) {
-        if (unroll >= 4) HD_RED(4, false, nullptr, mbits); else HD_RED(2, false, nullptr, mbits);
+        if (unroll >= 4) { HD_RED(4, false, nullptr, mbits); } else { HD_RED(2, false, nullptr, mbits); }
     } else if (unroll > 1 && !ys && out) {
-        if (unroll >= 4) HD_RED(4, false, BF(out), nomask); else HD_RED(2, false, BF(out), nomask);
+        if (unroll >= 4) { HD_RED(4, false, BF(out), nomask); } else { HD_RED(2, false, BF(out), nomask); }
     } else if (unroll > 1 && !ys) {
-        if (unroll >= 4) HD_RED(4, true, nullptr, nomask); else HD_RED(2, true, nullptr, nomask);
+        if (unroll >= 4) { HD_RED(4, true, nullptr, nomask); } else { HD_RED(2, true, nullptr, nomask); }
     }
 #undef HD_RED
     else if (mbits)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), nullptr,
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
-                                     mbits));
+                                     mbits, rev));
     else if (ys && out)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, false>, blocks, 256, smem, stream, BF(dout), BF(out),
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin,
-                                     static_cast<const uint8_t*>(nullptr)));
+                                     static_cast<const uint8_t*>(nullptr), rev));
     else if (ys)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<true, true>, blocks, 256, smem, stream, BF(dout), nullptr,
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), BF(ys), sums, np, C, fin,
-                                     static_cast<const uint8_t*>(nullptr)));
+                                     static_cast<const uint8_t*>(nullptr), rev));
     else if (out)
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, false>, blocks, 256, smem, stream, BF(dout), BF(out),
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
-                                     static_cast<const uint8_t*>(nullptr)));
+                                     static_cast<const uint8_t*>(nullptr), rev));
     else
         HD_CHECK_CUDA(::hd::launch_k(bn_bwd_reduce_kernel<false, true>, blocks, 256, smem, stream, BF(dout), nullptr,
                                      act_scale, act_shift, act_scale_s, act_shift_s, BF(y), nullptr, sums, np, C, fin,
-                                     static_cast<const uint8_t*>(nullptr)));
+                                     static_cast<const uint8_t*>(nullptr), rev));
     HD_CHECK_CUDA(cudaGetLastError()); ::hd::count_launch();
     return HD_OK;
 }
@@ -1286,16 +1337,17 @@ static int bn_bwd_apply_impl(cvp dout, cvp out, const uint8_t* mbits, const floa
                "bn_bwd_apply: rebuilding the mask of a two-branch tail needs the skip branch's scale/shift too");
     const size_t nvec = static_cast<size_t>(npix) * (C / 8);
     if (nvec == 0) return HD_OK;
-    const int blocks = ew_blocks(nvec);
+    int blocks = ew_blocks(nvec);
     const int unroll = bn_bwd_unroll();
 #define HD_APP(U_, G_)                                                                                               \
+    blocks = sweep_grid(bn_bwd_apply_kernel<false, G_, U_>, nvec, 256, 0, 16);                                       \
     HD_CHECK_CUDA(::hd::launch_k(bn_bwd_apply_kernel<false, G_, U_>, blocks, 256, 0, stream, BF(dout), BF(out), act_scale, \
                                  act_shift, act_scale_s, act_shift_s, BF(y), coef, BFW(dy), nullptr, nullptr, nullptr,  \
                                  G_ ? BFW(gout) : nullptr, nvec, C, mbits))
     if (unroll > 1 && !ys && gout) {
-        if (unroll >= 4) HD_APP(4, true); else HD_APP(2, true);
+        if (unroll >= 4) { HD_APP(4, true); } else { HD_APP(2, true); }
     } else if (unroll > 1 && !ys) {
-        if (unroll >= 4) HD_APP(4, false); else HD_APP(2, false);
+        if (unroll >= 4) { HD_APP(4, false); } else { HD_APP(2, false); }
     }
 #undef HD_APP
     else if (ys && gout)

@@ -910,10 +910,12 @@ static void backward_impl(hd_net* n, const float* dlogits, int stages = 3) {
     // (HD_NO_POOL_BWD_FUSE=1: the separate hd_maxpool2_bwd_idx launch of the first version)
     static const bool no_pool_bwd_fuse = getenv("HD_NO_POOL_BWD_FUSE") != nullptr;
     const bool fold_pool = n->R1idx != nullptr && !no_pool_bwd_fuse;
-    bf16* dR1 = fold_pool ? nullptr : reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
-    if (fold_pool) {}
-    else if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
-    else RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    bf16* dR1 = nullptr;
+    if (!fold_pool) {
+        dR1 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 128)));
+        if (n->R1idx) RUN(hd_maxpool2_bwd_idx(n->R1idx, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+        else RUN(hd_maxpool2_bwd(n->res[n->r_pre1].Out, dP, nullptr, nullptr, dR1, B, H2, W2, 128, n->stream));
+    }
     phase_mark(n, "pool bwd");
     bf16* dZ0 = reinterpret_cast<bf16*>(n->bw.alloc(act_bytes(B, H2, W2, 64)));
     residual_bwd(n, n->r_pre1, fold_pool ? dP : dR1, dZ0, B, fold_pool ? n->R1idx : nullptr);

@@ -117,3 +117,25 @@ def test_reference_staging_and_shims_layout():
         diff = open(os.path.join(refload.REF, "patched", "squeeze_patch.diff")).read()
         changed = [l for l in diff.splitlines() if l[:1] in "+-" and l[:3] not in ("+++", "---")]
         assert len(changed) == 4 and all("squeeze" in l for l in changed)       # the one-token fix, twice
+
+
+def test_documented_knobs_exist_in_the_sources():
+    """Every HD_* environment knob / macro the documents name (profiles/README.md, README.md)
+    is spelled the way the sources read it - a renamed knob would otherwise turn an A/B instruction into a silent no-op."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    named = set()
+    for doc in ("INTEGRATION.md", "DESIGN.md", os.path.join("profiles", "README.md"), "README.md"):
+        with open(os.path.join(root, doc)) as f:
+            named |= set(re.findall(r"\bHD_[A-Z0-9_]{3,}\b", f.read()))
+    text = []
+    pats = ["real_time_helmet_detection_b200/**/*", "tools/*.py", "tests/*.py", "include/*.h", "runner/*.cpp", "bench.py", "__graft_entry__.py"]
+    for pat in pats:
+        for path in glob.glob(os.path.join(root, pat), recursive=True):
+            if os.path.isfile(path) and path.endswith((".cu", ".cuh", ".h", ".py", ".cpp")):
+                with open(path, errors="ignore") as f:
+                    text.append(f.read())
+    text = "\n".join(text)
+    missing = sorted(k for k in named if k not in text)
+    assert not missing, missing
